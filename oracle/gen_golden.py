@@ -1,0 +1,68 @@
+"""Generate tests/golden/mixer_*.npz from the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE.  Imports /root/reference's ``modeling_nano.py`` (with the one-function pure-torch
+``rmsnorm_fn`` shim under oracle/_shim, because the file hard-imports mamba_ssm at :73-77), builds
+``NemotronHMamba2Mixer`` (modeling_nano.py:383-885) at small configs, runs its ``forward`` on CPU --
+which dispatches to ``torch_forward`` (:862-885 -> :671-859) -- and stores inputs, parameters, the output
+and both cache states.  /root/reference does not exist on the GPU box; the committed .npz files do.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/mixer_*.npz
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/timeviper/model/llm/llm_repo"
+
+CASES = {
+    # name: (hidden, H, P, G, N, Q, L, time_step_limit)
+    "g1_ragged300": (96, 4, 80, 1, 128, 128, 300, (0.0, float("inf"))),
+    "g1_exact256": (96, 4, 80, 1, 128, 128, 256, (0.0, float("inf"))),
+    "g2_literal_short100": (64, 4, 80, 2, 128, 128, 100, (0.0, float("inf"))),
+    "g1_dtlimit_q64": (64, 4, 16, 1, 32, 64, 200, (0.01, 0.2)),
+}
+
+
+def load_reference():
+    sys.path.insert(0, os.path.join(HERE, "_shim"))
+    sys.path.insert(0, REF)
+    import nano.modeling_nano as mn
+    from nano.configuration_nano import NemotronHConfig
+    return mn, NemotronHConfig
+
+
+def main():
+    mn, Cfg = load_reference()
+    out_dir = os.path.join(HERE, "..", "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (hidden, H, P, G, N, Q, L, lim) in CASES.items():
+        torch.manual_seed(1234)
+        cfg = Cfg(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, mamba_n_groups=G,
+                  ssm_state_size=N, mamba_chunk_size=Q, mamba_d_conv=4, mamba_dt_limit=lim,
+                  num_hidden_layers=2, hybrid_override_pattern="M-", layer_norm_epsilon=1e-5)
+        mixer = mn.NemotronHMamba2Mixer(cfg, layer_idx=0).float().eval()
+        with torch.no_grad():                      # make every term non-degenerate
+            mixer.A_log.copy_(torch.log(torch.rand(H) * 15 + 1))
+            mixer.dt_bias.copy_(torch.randn(H) * 0.5 - 2.0)
+            mixer.D.copy_(torch.randn(H))
+            mixer.norm.weight.copy_(1.0 + 0.1 * torch.randn(H * P))
+        hs = torch.randn(1, L, hidden)
+        cache = mn.HybridMambaAttentionDynamicCache(cfg, batch_size=1, dtype=torch.float32)
+        with torch.no_grad():
+            out = mixer(hs, cache_params=cache, cache_position=torch.arange(L))
+        blob = {k: v.detach().numpy() for k, v in mixer.state_dict().items()}
+        blob.update(hidden_states=hs.numpy(), out=out.numpy(),
+                    conv_state=cache.conv_states[0].numpy(), ssm_state=cache.ssm_states[0].numpy(),
+                    dims=np.array([hidden, H, P, G, N, Q, L], dtype=np.int64),
+                    time_step_limit=np.array(lim, dtype=np.float64))
+        path = os.path.join(out_dir, f"mixer_{name}.npz")
+        np.savez_compressed(path, **blob)
+        print(name, "out", tuple(out.shape), "ssm", tuple(cache.ssm_states[0].shape),
+              "conv", tuple(cache.conv_states[0].shape), "->", os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
