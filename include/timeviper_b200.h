@@ -1,0 +1,141 @@
+/*
+ * timeviper_b200 -- C ABI of the B200-native Mamba-2 mixer prefill path.
+ *
+ * The reference (xiaomi-research/timeviper) has no native code: its mixer calls module-level Python names
+ * bound to third-party wheels (timeviper/model/llm/llm_repo/nano/modeling_nano.py:60-97).  Each entry
+ * point below is what a binding for one of those names calls; timeviper_b200/ops.py is that binding
+ * (ctypes) and INTEGRATION.md shows how the reference rebinds its globals to it.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the library never allocates or frees device memory, never synchronises, never changes device:
+ *     outputs and workspaces are caller-allocated, work is enqueued on `stream` (a cudaStream_t);
+ *   - strides are in ELEMENTS of the tensor's dtype;
+ *   - return 0 on success, a negative tv_status otherwise; tv_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback.
+ */
+#ifndef TIMEVIPER_B200_H
+#define TIMEVIPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TV_ABI_VERSION 1
+
+typedef enum { TV_F32 = 0, TV_BF16 = 1 } tv_dtype;
+
+typedef enum {
+  TV_OK = 0,
+  TV_ERR_INVALID = -1,     /* bad shape / stride / alignment / dtype (Python raises ValueError)      */
+  TV_ERR_UNSUPPORTED = -2, /* valid request this build has no kernel for (NotImplementedError)        */
+  TV_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed (RuntimeError)                        */
+  TV_ERR_WORKSPACE = -4    /* workspace too small                                                      */
+} tv_status;
+
+int tv_abi_version(void);
+const char* tv_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * causal_conv1d_fn  (causal_conv1d 1.5.2; call site modeling_nano.py:619-624; positional form
+ * visualize/nano/my_ssd_combined.py:1606-1614).
+ *   y[b,c,t] = act(bias[c] + sum_k w[c,k] * x[b,c,t-(K-1)+k]),  x[t<0] = initial_states or 0.
+ * x and out are CHANNEL-LAST: element (b,c,t) at  b*batch_stride + t*seq_stride + c.
+ * initial_states / final_states: (batch, dim, width-1), contiguous, same dtype as x; may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  const void* weight;          /* (dim, width) contiguous, dtype of x                           */
+  const void* bias;            /* (dim,) or NULL                                                */
+  const void* initial_states;  /* (batch, dim, width-1) or NULL                                 */
+  void* out;
+  void* final_states;          /* (batch, dim, width-1) or NULL                                 */
+  int32_t batch, dim, seqlen, width;
+  int64_t x_batch_stride, x_seq_stride;
+  int64_t out_batch_stride, out_seq_stride;
+  int32_t silu;                /* 1: SiLU ("silu"/"swish"), 0: identity                          */
+  int32_t dtype;               /* tv_dtype of x / weight / bias / out                            */
+} tv_conv1d_params;
+
+int tv_causal_conv1d_fwd(const tv_conv1d_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * rmsnorm_fn (mamba_ssm.ops.triton.layernorm_gated; call site modeling_nano.py:372-380).
+ *   norm_before_gate=0:  u = x*silu(z);  out = u * rsqrt(mean_group(u^2)+eps) * w (+bias)
+ *   norm_before_gate=1:  out = (x * rsqrt(mean_group(x^2)+eps) * w (+bias)) * silu(z)
+ * x, z, out: (rows, d) with unit inner stride and the given row strides; z may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  const void* z;
+  const void* weight;          /* (d,)                                                           */
+  const void* bias;            /* (d,) or NULL                                                   */
+  void* out;
+  int64_t rows;
+  int32_t d, group_size;
+  int64_t x_row_stride, z_row_stride, out_row_stride;
+  float eps;
+  int32_t norm_before_gate;
+  int32_t dtype;               /* tv_dtype of x / z / weight / bias / out                        */
+} tv_rmsnorm_params;
+
+int tv_gated_rmsnorm_fwd(const tv_rmsnorm_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * mamba_chunk_scan_combined forward (mamba_ssm 2.2.5 ssd_combined; signature
+ * visualize/nano/my_ssd_combined.py:1270-1306, stages :743-843; call site modeling_nano.py:639-653).
+ *   x (b,L,H,P)  dt (b,L,H)  A (H,) f32  B,C (b,L,G,N)  D (H,) or (H,P) f32  z (b,L,H,P)
+ *   dt_bias (H,) f32   initial_states (b,H,P,N) f32   ->   out (b,L,H,P) x-dtype, final_states (b,H,P,N) f32
+ * Head h reads group h / (H/G).  x/z/B/C have unit stride on their last dim; out is contiguous.
+ * `mode`: TV_SSD_FULL computes out (+final_states); TV_SSD_STATE_ONLY computes only final_states and
+ * chunk_logdecay_sum (the shard summary of the sequence-sharded path) and touches neither out, C, D nor z.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum { TV_SSD_FULL = 0, TV_SSD_STATE_ONLY = 1 } tv_ssd_mode;
+
+typedef struct {
+  const void* x; const void* dt; const float* A; const void* B; const void* C;
+  const float* D;              /* NULL, (H,) or (H,P) -- see d_has_hdim                          */
+  const void* z;               /* NULL or (b,L,H,P)                                              */
+  const float* dt_bias;        /* NULL or (H,)                                                   */
+  const float* initial_states; /* NULL or (b,H,P,N) contiguous                                   */
+  void* out;                   /* (b,L,H,P) contiguous                                           */
+  float* final_states;         /* NULL or (b,H,P,N) contiguous                                   */
+  float* logdecay_sum;         /* NULL or (b,H): sum over the sequence of dt*A (log of the decay) */
+  int32_t batch, seqlen, nheads, headdim, ngroups, dstate, chunk_size;
+  int64_t x_batch_stride, x_seq_stride, x_head_stride;
+  int64_t dt_batch_stride, dt_seq_stride, dt_head_stride;
+  int64_t b_batch_stride, b_seq_stride, b_group_stride;
+  int64_t c_batch_stride, c_seq_stride, c_group_stride;
+  int64_t z_batch_stride, z_seq_stride, z_head_stride;
+  int32_t d_has_hdim;          /* 1 if D is (H,P)                                                */
+  int32_t dt_softplus;
+  float dt_min, dt_max;        /* dt_limit; (0, +inf) is a no-op clamp                           */
+  int32_t dtype;               /* tv_dtype of x / dt / B / C / z / out                           */
+  int32_t mode;                /* tv_ssd_mode                                                    */
+  int32_t force_simt;          /* 1: use the fp32 CUDA-core kernels even where a tcgen05 kernel exists */
+} tv_ssd_params;
+
+/* Bytes of caller-allocated scratch tv_ssd_chunk_scan_fwd needs for these dims (0 is possible). */
+size_t tv_ssd_workspace_bytes(const tv_ssd_params* p);
+int tv_ssd_chunk_scan_fwd(const tv_ssd_params* p, void* workspace, size_t workspace_bytes, void* stream);
+/* Which kernel family tv_ssd_chunk_scan_fwd would run: 0 = fp32 CUDA-core, 1 = tcgen05/TMEM/TMA. */
+int tv_ssd_kernel_family(const tv_ssd_params* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sequence-sharded prefill: fold the gathered per-shard summaries into the state entering shard `rank`.
+ *   S_in(0) = initial (or 0);  S_in(r+1) = exp(logdecay[r]) * S_in(r) + states[r]
+ * states: (world, b, H, P, N) f32, logdecay: (world, b, H) f32 (as gathered), out: (b, H, P, N) f32.
+ * New work (the reference has no sequence parallelism); the hook it plugs into is
+ * the `initial_states=` argument of mamba_chunk_scan_combined (my_ssd_combined.py:1280,1300).
+ * ------------------------------------------------------------------------------------------- */
+int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, const float* initial,
+                                float* out, int32_t rank, int32_t batch, int32_t nheads,
+                                int32_t headdim, int32_t dstate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIMEVIPER_B200_H */

@@ -1,0 +1,114 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, the Python operators keep the reference's names/signatures and fail loudly without a GPU."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for f in os.listdir(inc):
+        if f.endswith(".h"):
+            src = open(os.path.join(inc, f)).read()
+            names |= set(re.findall(r"\b(tv_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    import timeviper_b200._lib as L
+    lib = L.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 8
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert set(declared) == set(L.EXPORTS)
+    assert lib.tv_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors must have the C layout: compile-free check through field counts and sizes."""
+    import timeviper_b200._lib as L
+    assert ctypes.sizeof(L.ConvParams) == 6 * 8 + 4 * 4 + 4 * 8 + 2 * 4
+    assert ctypes.sizeof(L.RmsnormParams) == 5 * 8 + 8 + 2 * 4 + 3 * 8 + 3 * 4 + 4   # + tail padding
+    assert ctypes.sizeof(L.SsdParams) == 12 * 8 + 7 * 4 + 4 + 15 * 8 + 2 * 4 + 2 * 4 + 3 * 4 + 4
+
+
+def test_null_and_invalid_arguments_return_error_codes_without_touching_a_gpu():
+    import timeviper_b200._lib as L
+    lib = L.load()
+    assert lib.tv_causal_conv1d_fwd(None, None) == L.TV_ERR_INVALID
+    assert b"null" in lib.tv_last_error()
+    p = L.ConvParams(batch=1, dim=12, seqlen=4, width=4, dtype=L.TV_BF16)
+    assert lib.tv_causal_conv1d_fwd(ctypes.byref(p), None) == L.TV_ERR_INVALID
+    q = L.SsdParams(batch=1, seqlen=8, nheads=3, headdim=8, ngroups=2, dstate=8, chunk_size=64)
+    assert lib.tv_ssd_chunk_scan_fwd(ctypes.byref(q), None, 0, None) == L.TV_ERR_INVALID   # 3 % 2 != 0
+    assert lib.tv_gated_rmsnorm_fwd(None, None) == L.TV_ERR_INVALID
+
+
+def test_operator_signatures_match_reference_call_sites():
+    import timeviper_b200 as tv
+    # causal_conv1d 1.5.x: (x, weight, bias, seq_idx, initial_states, return_final_states, final_states_out, activation)
+    assert list(inspect.signature(tv.causal_conv1d_fn).parameters) == [
+        "x", "weight", "bias", "seq_idx", "initial_states", "return_final_states", "final_states_out", "activation"]
+    # visualize/nano/my_ssd_combined.py:1270-1287
+    sig = list(inspect.signature(tv.mamba_chunk_scan_combined).parameters)
+    assert sig[:16] == ["x", "dt", "A", "B", "C", "chunk_size", "D", "z", "dt_bias", "initial_states", "seq_idx",
+                        "cu_seqlens", "dt_softplus", "dt_limit", "return_final_states", "return_varlen_states"]
+    # modeling_nano.py:372-380 keyword call
+    assert list(inspect.signature(tv.rmsnorm_fn).parameters) == [
+        "x", "weight", "bias", "z", "eps", "group_size", "norm_before_gate", "upcast"]
+    # modeling_nano.py:862-869
+    assert list(inspect.signature(tv.Mamba2MixerPrefill.forward).parameters) == [
+        "self", "hidden_states", "cache_params", "cache_position", "attention_mask", "seq_idx"]
+
+
+def test_no_cpu_fallback():
+    import timeviper_b200 as tv
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tv.causal_conv1d_fn(torch.zeros(1, 8, 4), torch.zeros(8, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tv.rmsnorm_fn(torch.zeros(2, 8), torch.ones(8), None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tv.mamba_chunk_scan_combined(torch.zeros(1, 4, 2, 8), torch.zeros(1, 4, 2), torch.zeros(2),
+                                     torch.zeros(1, 4, 1, 8), torch.zeros(1, 4, 1, 8), 64)
+    m = tv.Mamba2MixerPrefill(tv.Mamba2Config(hidden_size=32, mamba_num_heads=2, mamba_head_dim=8, n_groups=1,
+                                              ssm_state_size=8, chunk_size=64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 4, 32))
+    for fn in (tv.causal_conv1d_update, tv.selective_state_update, tv.mamba_split_conv1d_scan_combined):
+        with pytest.raises(NotImplementedError):
+            fn()
+
+
+def test_mixer_loads_reference_state_dict(golden_dir):
+    """Parameter names/shapes are the reference's (modeling_nano.py:414-451): its state_dict loads strictly."""
+    import timeviper_b200 as tv
+    z = np.load(os.path.join(golden_dir, "mixer_g1_ragged300.npz"))
+    hidden, H, P, G, N, Q, L = [int(v) for v in z["dims"]]
+    m = tv.Mamba2MixerPrefill(tv.Mamba2Config(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, n_groups=G,
+                                              ssm_state_size=N, chunk_size=Q))
+    keys = ["in_proj.weight", "conv1d.weight", "conv1d.bias", "dt_bias", "A_log", "D", "norm.weight", "out_proj.weight"]
+    sd = {k: torch.from_numpy(z[k]) for k in keys}
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+
+
+def test_patch_reference_rebinds_all_gate_names():
+    import types
+    import timeviper_b200 as tv
+    mod = types.SimpleNamespace(causal_conv1d_fn=None, causal_conv1d_update=None, mamba_chunk_scan_combined=None,
+                                mamba_split_conv1d_scan_combined=None, selective_state_update=None, rmsnorm_fn=None,
+                                is_fast_path_available=False)
+    tv.patch_reference(mod)
+    assert mod.is_fast_path_available
+    assert all((mod.selective_state_update, mod.mamba_chunk_scan_combined, mod.mamba_split_conv1d_scan_combined,
+                mod.causal_conv1d_fn, mod.causal_conv1d_update))                # the gate of modeling_nano.py:89-97
+    assert mod.causal_conv1d_fn is tv.causal_conv1d_fn and mod.rmsnorm_fn is tv.rmsnorm_fn

@@ -1,0 +1,55 @@
+"""Dimensions of the Mamba-2 mixer, with the reference's attribute names
+(timeviper/model/llm/llm_repo/nano/configuration_nano.py:133-258; read by the mixer at
+modeling_nano.py:393-411)."""
+from dataclasses import dataclass, field
+from typing import Tuple
+
+
+@dataclass
+class Mamba2Config:
+    hidden_size: int = 4480
+    mamba_num_heads: int = 128
+    mamba_head_dim: int = 80
+    n_groups: int = 8
+    ssm_state_size: int = 128
+    chunk_size: int = 128
+    conv_kernel: int = 4
+    layer_norm_epsilon: float = 1e-5
+    time_step_limit: Tuple[float, float] = (0.0, float("inf"))
+    time_step_min: float = 0.001
+    time_step_max: float = 0.1
+    time_step_floor: float = 1e-4
+    use_conv_bias: bool = True
+    use_bias: bool = False
+    mamba_hidden_act: str = "silu"
+    num_hidden_layers: int = 56
+
+    @property
+    def intermediate_size(self):
+        return self.mamba_num_heads * self.mamba_head_dim
+
+    @property
+    def conv_dim(self):
+        return self.intermediate_size + 2 * self.n_groups * self.ssm_state_size
+
+    @property
+    def projection_size(self):
+        return self.intermediate_size + self.conv_dim + self.mamba_num_heads
+
+    @classmethod
+    def nanov2_9b(cls):
+        """NVIDIA-Nemotron-Nano-9B-v2 Mamba-2 layer (SURVEY.md section 8 header: the checkpoint's config.json
+        is not in the reference tree; every field is overridable)."""
+        return cls()
+
+    @classmethod
+    def small(cls, n_groups=1):
+        """BASELINE.json configs[0]: the reference's CPU-runnable small config."""
+        return cls(hidden_size=512, mamba_num_heads=16, mamba_head_dim=80, n_groups=n_groups,
+                   ssm_state_size=128, chunk_size=128)
+
+    @classmethod
+    def from_hf(cls, cfg):
+        """From a reference NemotronHConfig (or anything with the same attributes)."""
+        names = [f for f in cls.__dataclass_fields__]
+        return cls(**{n: getattr(cfg, n) for n in names if hasattr(cfg, n)})

@@ -1,0 +1,158 @@
+// Depthwise causal conv1d (+bias, +SiLU), channel-last, for sm_100a.
+//
+// Replaces causal_conv1d_fn (causal_conv1d 1.5.2) at the reference call site
+// timeviper/model/llm/llm_repo/nano/modeling_nano.py:619-624.  The input there is a strided channel-last
+// VIEW into the in_proj output (row stride 22656 elements, base offset 10240): the kernel honours
+// arbitrary batch/row strides and only requires unit channel stride and 16-byte alignment.
+//
+// Roofline: pure HBM streaming, 2 * dim * sizeof(T) bytes per token (49,152 B at dim 12288, bf16).
+// Layout/tiling: one thread owns 16 bytes of channels (8 bf16) and walks TOK consecutive tokens with the
+// K-1 previous rows kept in registers, so every x element is read once per CTA (halo re-read = (K-1)/TOK,
+// served from L2); a warp reads/writes 512 contiguous bytes per token row.
+#include "common.cuh"
+
+namespace tv {
+
+constexpr int CONV_THREADS = 128;
+constexpr int CONV_TOK = 64;   // tokens per CTA along the sequence
+constexpr int CONV_U = 4;      // independent 16-byte loads in flight per thread
+
+template <typename T, int K, bool SILU>
+__global__ void __launch_bounds__(CONV_THREADS)
+conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T* __restrict__ bias,
+                  const T* __restrict__ init, T* __restrict__ out, T* __restrict__ fin,
+                  int dim, int L, int64_t xbs, int64_t xss, int64_t obs, int64_t oss) {
+  constexpr int V = Vec16<T>::N;
+  constexpr bool FAST = sizeof(T) == 2;
+  const int c0 = (blockIdx.x * CONV_THREADS + threadIdx.x) * V;
+  if (c0 >= dim) return;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * CONV_TOK;
+  const int t1 = min(t0 + CONV_TOK, L);
+  x += (int64_t)b * xbs + c0;
+  out += (int64_t)b * obs + c0;
+
+  // weights (dim, K) row-major: this thread's V*K values are contiguous -> K 16-byte loads
+  float w[K][V], bv[V];
+  {
+    float flat[K * V];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      float tmp[V];
+      load16<T>(weight + (int64_t)c0 * K + i * V, tmp);
+#pragma unroll
+      for (int j = 0; j < V; ++j) flat[i * V + j] = tmp[j];
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int k = 0; k < K; ++k) w[k][v] = flat[v * K + k];
+    if (bias != nullptr) load16<T>(bias + c0, bv);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) bv[v] = 0.f;
+    }
+  }
+
+  // the K-1 rows preceding t0
+  float win[K - 1][V];
+#pragma unroll
+  for (int j = 0; j < K - 1; ++j) {
+    const int t = t0 - (K - 1) + j;
+    if (t >= 0) {
+      load16<T>(x + (int64_t)t * xss, win[j]);
+    } else if (init != nullptr) {  // (b, dim, K-1): column t+(K-1) of the carried-in state
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        win[j][v] = to_f32<T>(init[((int64_t)b * dim + c0 + v) * (K - 1) + (t + K - 1)]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) win[j][v] = 0.f;
+    }
+  }
+
+  for (int tt = t0; tt < t1; tt += CONV_U) {
+    float xin[CONV_U][V];
+#pragma unroll
+    for (int u = 0; u < CONV_U; ++u)
+      if (tt + u < t1) load16<T>(x + (int64_t)(tt + u) * xss, xin[u]);
+#pragma unroll
+    for (int u = 0; u < CONV_U; ++u) {
+      if (tt + u < t1) {
+        float o[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float acc = bv[v];
+#pragma unroll
+          for (int k = 0; k < K - 1; ++k) acc = fmaf(w[k][v], win[k][v], acc);
+          acc = fmaf(w[K - 1][v], xin[u][v], acc);
+          o[v] = SILU ? silu<FAST>(acc) : acc;
+        }
+        store16<T>(out + (int64_t)(tt + u) * oss, o);
+#pragma unroll
+        for (int k = 0; k < K - 2; ++k)
+#pragma unroll
+          for (int v = 0; v < V; ++v) win[k][v] = win[k + 1][v];
+#pragma unroll
+        for (int v = 0; v < V; ++v) win[K - 2][v] = xin[u][v];
+      }
+    }
+  }
+
+  // carried-out state = the last K-1 input columns (includes carried-in columns when L < K-1)
+  if (fin != nullptr && t1 == L) {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int j = 0; j < K - 1; ++j)
+        fin[((int64_t)b * dim + c0 + v) * (K - 1) + j] = from_f32<T>(win[j][v]);
+  }
+}
+
+template <typename T, int K>
+static int launch_conv(const tv_conv1d_params& p, cudaStream_t s) {
+  constexpr int V = Vec16<T>::N;
+  dim3 grid((unsigned)ceil_div(p.dim / V, CONV_THREADS), (unsigned)ceil_div(p.seqlen, CONV_TOK), p.batch);
+  auto kern = p.silu ? conv1d_fwd_kernel<T, K, true> : conv1d_fwd_kernel<T, K, false>;
+  kern<<<grid, CONV_THREADS, 0, s>>>((const T*)p.x, (const T*)p.weight, (const T*)p.bias,
+                                     (const T*)p.initial_states, (T*)p.out, (T*)p.final_states, p.dim,
+                                     p.seqlen, p.x_batch_stride, p.x_seq_stride, p.out_batch_stride,
+                                     p.out_seq_stride);
+  TV_CUDA_OK(cudaGetLastError());
+  return TV_OK;
+}
+
+template <typename T>
+static int dispatch_width(const tv_conv1d_params& p, cudaStream_t s) {
+  switch (p.width) {
+    case 2: return launch_conv<T, 2>(p, s);
+    case 3: return launch_conv<T, 3>(p, s);
+    case 4: return launch_conv<T, 4>(p, s);
+    default:
+      set_error("causal_conv1d: width %d unsupported (2..4)", p.width);
+      return TV_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace tv
+
+extern "C" int tv_causal_conv1d_fwd(const tv_conv1d_params* p, void* stream) {
+  using namespace tv;
+  TV_CHECK_ARG(p != nullptr, "causal_conv1d: null params");
+  TV_CHECK_ARG(p->x && p->weight && p->out, "causal_conv1d: x, weight and out must be non-null");
+  TV_CHECK_ARG(p->batch > 0 && p->dim > 0 && p->seqlen > 0, "causal_conv1d: empty problem (b=%d dim=%d L=%d)",
+               p->batch, p->dim, p->seqlen);
+  TV_CHECK_ARG(p->dtype == TV_F32 || p->dtype == TV_BF16, "causal_conv1d: dtype %d", p->dtype);
+  const int V = p->dtype == TV_BF16 ? 8 : 4;
+  const int esz = p->dtype == TV_BF16 ? 2 : 4;
+  TV_CHECK_ARG(p->dim % V == 0, "causal_conv1d: dim %d must be a multiple of %d", p->dim, V);
+  TV_CHECK_ARG(p->x_seq_stride % V == 0 && p->x_batch_stride % V == 0 && p->out_seq_stride % V == 0 &&
+                   p->out_batch_stride % V == 0,
+               "causal_conv1d: strides must be multiples of %d elements (16 bytes)", V);
+  TV_CHECK_ARG(((uintptr_t)p->x % 16 == 0) && ((uintptr_t)p->out % 16 == 0) && ((uintptr_t)p->weight % 16 == 0) &&
+                   (p->bias == nullptr || (uintptr_t)p->bias % 16 == 0),
+               "causal_conv1d: x/out/weight/bias must be 16-byte aligned");
+  (void)esz;
+  cudaStream_t s = (cudaStream_t)stream;
+  return p->dtype == TV_BF16 ? dispatch_width<__nv_bfloat16>(*p, s) : dispatch_width<float>(*p, s);
+}

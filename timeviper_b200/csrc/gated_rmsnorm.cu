@@ -1,0 +1,125 @@
+// z-gated grouped RMSNorm for sm_100a.
+//
+// Replaces mamba_ssm's Triton rmsnorm_fn (layernorm_gated) at the reference call site
+// timeviper/model/llm/llm_repo/nano/modeling_nano.py:372-380 (norm_before_gate=False, group = d_inner/G).
+// The gate z is a strided VIEW into the in_proj output (row stride 22656): only unit inner stride and
+// 16-byte alignment are required.
+//
+// Roofline: HBM streaming, 3 * d * sizeof(T) bytes per row (61,440 B at d = 10240, bf16).
+// One warp owns one (row, group): x and z are read once with 16-byte loads into registers, the sum of
+// squares is a warp-shuffle reduction, the output is written with 16-byte stores.  8 warps per CTA.
+#include "common.cuh"
+
+namespace tv {
+
+constexpr int NORM_WARPS = 8;
+constexpr int NORM_MAX_GROUP = 2048;  // elements of one group cached in a warp's registers (64 per lane)
+
+template <typename T, bool HAS_Z, bool NORM_BEFORE_GATE, bool HAS_BIAS>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+gated_rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ z, const T* __restrict__ w,
+                     const T* __restrict__ bias, T* __restrict__ out, int64_t rows, int ngroups,
+                     int group_size, int64_t xrs, int64_t zrs, int64_t ors, float eps) {
+  constexpr int V = Vec16<T>::N;
+  constexpr int NORM_MAXV = NORM_MAX_GROUP / 32 / V;
+  constexpr bool FAST = sizeof(T) == 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
+  if (item >= rows * ngroups) return;
+  const int64_t row = item / ngroups;
+  const int g = (int)(item - row * ngroups);
+  const int nvec = group_size / V;
+  const T* xp = x + row * xrs + (int64_t)g * group_size;
+  const T* zp = HAS_Z ? z + row * zrs + (int64_t)g * group_size : nullptr;
+  const T* wp = w + (int64_t)g * group_size;
+  T* op = out + row * ors + (int64_t)g * group_size;
+
+  float u[NORM_MAXV][V];   // x (norm_before_gate) or x*silu(z)
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      load16<T>(xp + vi * V, u[i]);
+      if (HAS_Z && !NORM_BEFORE_GATE) {
+        float zz[V];
+        load16<T>(zp + vi * V, zz);
+#pragma unroll
+        for (int j = 0; j < V; ++j) u[i][j] *= silu<FAST>(zz[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) ss = fmaf(u[i][j], u[i][j], ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / (float)group_size + eps);
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      float ww[V], o[V];
+      load16<T>(wp + vi * V, ww);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = u[i][j] * rstd * ww[j];
+      if (HAS_BIAS) {
+        float bb[V];
+        load16<T>(bias + (int64_t)g * group_size + vi * V, bb);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] += bb[j];
+      }
+      if (HAS_Z && NORM_BEFORE_GATE) {
+        float zz[V];
+        load16<T>(zp + vi * V, zz);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] *= silu<FAST>(zz[j]);
+      }
+      store16<T>(op + vi * V, o);
+    }
+  }
+}
+
+template <typename T>
+static int launch_norm(const tv_rmsnorm_params& p, cudaStream_t s) {
+  const int ngroups = p.d / p.group_size;
+  const int64_t items = p.rows * ngroups;
+  dim3 grid((unsigned)ceil_div(items, NORM_WARPS));
+  const bool hz = p.z != nullptr, nbg = p.norm_before_gate != 0, hb = p.bias != nullptr;
+#define TV_NORM_LAUNCH(HZ, NBG, HB)                                                                       \
+  gated_rmsnorm_kernel<T, HZ, NBG, HB><<<grid, NORM_WARPS * 32, 0, s>>>(                                   \
+      (const T*)p.x, (const T*)p.z, (const T*)p.weight, (const T*)p.bias, (T*)p.out, p.rows, ngroups,      \
+      p.group_size, p.x_row_stride, p.z_row_stride, p.out_row_stride, p.eps)
+  if (hz && !nbg && !hb) TV_NORM_LAUNCH(true, false, false);
+  else if (hz && !nbg && hb) TV_NORM_LAUNCH(true, false, true);
+  else if (hz && nbg && !hb) TV_NORM_LAUNCH(true, true, false);
+  else if (hz && nbg && hb) TV_NORM_LAUNCH(true, true, true);
+  else if (!hb) TV_NORM_LAUNCH(false, true, false);
+  else TV_NORM_LAUNCH(false, true, true);
+#undef TV_NORM_LAUNCH
+  TV_CUDA_OK(cudaGetLastError());
+  return TV_OK;
+}
+
+}  // namespace tv
+
+extern "C" int tv_gated_rmsnorm_fwd(const tv_rmsnorm_params* p, void* stream) {
+  using namespace tv;
+  TV_CHECK_ARG(p != nullptr, "rmsnorm: null params");
+  TV_CHECK_ARG(p->x && p->weight && p->out, "rmsnorm: x, weight and out must be non-null");
+  TV_CHECK_ARG(p->rows > 0 && p->d > 0, "rmsnorm: empty problem (rows=%lld d=%d)", (long long)p->rows, p->d);
+  TV_CHECK_ARG(p->dtype == TV_F32 || p->dtype == TV_BF16, "rmsnorm: dtype %d", p->dtype);
+  const int V = p->dtype == TV_BF16 ? 8 : 4;
+  TV_CHECK_ARG(p->group_size > 0 && p->d % p->group_size == 0, "rmsnorm: group_size %d must divide d %d",
+               p->group_size, p->d);
+  TV_CHECK_ARG(p->group_size % V == 0, "rmsnorm: group_size %d must be a multiple of %d", p->group_size, V);
+  if (p->group_size > NORM_MAX_GROUP) {
+    set_error("rmsnorm: group_size %d > %d unsupported", p->group_size, NORM_MAX_GROUP);
+    return TV_ERR_UNSUPPORTED;
+  }
+  TV_CHECK_ARG(p->x_row_stride % V == 0 && p->out_row_stride % V == 0 && (p->z == nullptr || p->z_row_stride % V == 0),
+               "rmsnorm: row strides must be multiples of %d elements (16 bytes)", V);
+  TV_CHECK_ARG(((uintptr_t)p->x % 16 == 0) && ((uintptr_t)p->out % 16 == 0) && ((uintptr_t)p->weight % 16 == 0) &&
+                   ((uintptr_t)p->z % 16 == 0) && ((uintptr_t)p->bias % 16 == 0),
+               "rmsnorm: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  return p->dtype == TV_BF16 ? launch_norm<__nv_bfloat16>(*p, s) : launch_norm<float>(*p, s);
+}

@@ -1,0 +1,132 @@
+"""Drop-in for the prefill branch of ``NemotronHMamba2Mixer``
+(timeviper/model/llm/llm_repo/nano/modeling_nano.py:383-885).
+
+Same parameter names (so the reference state_dict loads unchanged), same ``forward`` signature (:862-869),
+same cache side effects (conv state (b, conv_dim, K) of pre-conv inputs :596-610; fp32 ssm state (b,H,P,N)
+:656-659).  in_proj / out_proj stay on cuBLAS (plain library GEMMs); the three stages between them run on
+this package's sm_100a kernels.  Decode (cache_position[0] > 0, :484-546) and the training fused path
+(:560-580) are outside the prefill path and raise.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .config import Mamba2Config
+
+
+class MambaRMSNormGated(nn.Module):
+    """modeling_nano.py:363-380."""
+
+    def __init__(self, hidden_size, group_size, eps=1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+        self.group_size = group_size
+
+    def forward(self, hidden_states, gate=None):
+        return ops.rmsnorm_fn(x=hidden_states, weight=self.weight, bias=None, z=gate, eps=self.variance_epsilon,
+                              group_size=self.group_size, norm_before_gate=False)
+
+
+class Mamba2MixerPrefill(nn.Module):
+    def __init__(self, config: Mamba2Config, layer_idx: int = 0):
+        super().__init__()
+        self.config = config
+        self.num_heads = config.mamba_num_heads
+        self.hidden_size = config.hidden_size
+        self.ssm_state_size = config.ssm_state_size
+        self.conv_kernel_size = config.conv_kernel
+        self.intermediate_size = config.mamba_num_heads * config.mamba_head_dim
+        self.layer_idx = layer_idx
+        self.use_conv_bias = config.use_conv_bias
+        self.activation = config.mamba_hidden_act
+        self.layer_norm_epsilon = config.layer_norm_epsilon
+        self.n_groups = config.n_groups
+        self.head_dim = config.mamba_head_dim
+        self.chunk_size = config.chunk_size
+        self.time_step_limit = tuple(config.time_step_limit)
+        self.conv_dim = self.intermediate_size + 2 * self.n_groups * self.ssm_state_size
+        self.conv1d = nn.Conv1d(self.conv_dim, self.conv_dim, bias=config.use_conv_bias,
+                                kernel_size=config.conv_kernel, groups=self.conv_dim,
+                                padding=config.conv_kernel - 1)
+        projection_size = self.intermediate_size + self.conv_dim + self.num_heads
+        self.in_proj = nn.Linear(self.hidden_size, projection_size, bias=config.use_bias)
+        self.dt_bias = nn.Parameter(torch.ones(self.num_heads))
+        self.A_log = nn.Parameter(torch.log(torch.arange(1, self.num_heads + 1, dtype=torch.float32)))
+        self.norm = MambaRMSNormGated(self.intermediate_size, eps=self.layer_norm_epsilon,
+                                      group_size=self.intermediate_size // self.n_groups)
+        self.D = nn.Parameter(torch.ones(self.num_heads))
+        self.out_proj = nn.Linear(self.intermediate_size, self.hidden_size, bias=config.use_bias)
+        if self.activation not in ("silu", "swish"):
+            raise NotImplementedError("the prefill kernels implement the silu/swish conv activation only")
+
+    @torch.no_grad()
+    def reset_parameters_like_reference(self, generator=None):
+        """_init_weights, modeling_nano.py:1339-1383 (dt_bias = softplus^-1 of a log-uniform dt; out_proj
+        rescaled by 1/sqrt(n_layers))."""
+        c = self.config
+        dt = torch.exp(torch.rand(self.num_heads, generator=generator)
+                       * (math.log(c.time_step_max) - math.log(c.time_step_min))
+                       + math.log(c.time_step_min)).clamp(min=c.time_step_floor)
+        self.dt_bias.copy_((dt + torch.log(-torch.expm1(-dt))).to(self.dt_bias))
+        nn.init.kaiming_uniform_(self.out_proj.weight, a=math.sqrt(5))
+        self.out_proj.weight /= math.sqrt(c.num_hidden_layers)
+
+    # -- the three-kernel core, on an already projected input (what bench.py's `value` times) ------------
+    def scan_core(self, projected_states, cache_params=None, conv_initial_states=None, ssm_initial_states=None,
+                  return_states=False):
+        """projected_states (b, L, d_inner + conv_dim + H) -> normed scan output (b, L, d_inner)."""
+        batch_size, seq_len, _ = projected_states.shape
+        gts = self.n_groups * self.ssm_state_size
+        gate, hidden_states_B_C, dt = projected_states.split(
+            [self.intermediate_size, self.conv_dim, self.num_heads], dim=-1)
+        if cache_params is not None:                                            # :596-610
+            xt = hidden_states_B_C.transpose(1, 2)
+            conv_states = nn.functional.pad(xt, (cache_params.conv_kernel_size - xt.shape[-1], 0))
+            cache_params.update_conv_state(layer_idx=self.layer_idx, new_conv_state=conv_states, cache_init=True)
+        hidden_states_B_C = ops.causal_conv1d_fn(                               # :619-624
+            x=hidden_states_B_C.transpose(1, 2), weight=self.conv1d.weight.squeeze(1), bias=self.conv1d.bias,
+            initial_states=conv_initial_states, activation=self.activation).transpose(1, 2)
+        hidden_states, B, C = torch.split(hidden_states_B_C, [self.intermediate_size, gts, gts], dim=-1)
+        A = -torch.exp(self.A_log.float())                                      # :550-552
+        scan_output, ssm_state = ops.mamba_chunk_scan_combined(                 # :639-653
+            hidden_states.view(batch_size, seq_len, -1, self.head_dim), dt, A,
+            B.view(batch_size, seq_len, self.n_groups, -1), C.view(batch_size, seq_len, self.n_groups, -1),
+            chunk_size=self.chunk_size, D=self.D, z=None, seq_idx=None, return_final_states=True,
+            dt_bias=self.dt_bias, dt_softplus=True, dt_limit=self.time_step_limit,
+            initial_states=ssm_initial_states)
+        if ssm_state is not None and cache_params is not None:                  # :656-659
+            cache_params.update_ssm_state(layer_idx=self.layer_idx, new_ssm_state=ssm_state)
+        scan_output = scan_output.view(batch_size, seq_len, -1)
+        scan_output = self.norm(scan_output, gate)                              # :664
+        return (scan_output, ssm_state) if return_states else scan_output
+
+    def forward(self, hidden_states, cache_params=None, cache_position=None, attention_mask=None, seq_idx=None):
+        if not hidden_states.is_cuda:
+            raise RuntimeError("Mamba2MixerPrefill runs on CUDA only: there is no CPU fallback "
+                               "(the reference's torch_forward lives in oracle/ as a test oracle)")
+        if seq_idx is not None:
+            raise NotImplementedError("seq_idx (packed training samples) is outside the prefill path")
+        if cache_params is not None and cache_position is not None and cache_position[0] > 0:
+            raise NotImplementedError("single-token decode (modeling_nano.py:484-546) is outside the prefill path")
+        if attention_mask is not None and attention_mask.shape[1] > 1 and attention_mask.shape[0] > 1:
+            # apply_mask_to_padding_states, modeling_nano.py:189-201 (a no-op at batch 1)
+            hidden_states = (hidden_states * attention_mask[:, :, None]).to(hidden_states.dtype)
+        projected_states = self.in_proj(hidden_states)                          # :472
+        scan_output = self.scan_core(projected_states, cache_params)
+        return self.out_proj(scan_output)                                       # :667
+
+
+def patch_reference(modeling_nano):
+    """Rebind the module-level operator names the reference mixer calls (modeling_nano.py:60-97) to this
+    package, so an unmodified ``NemotronHMamba2Mixer.cuda_kernels_forward`` runs on the sm_100a kernels."""
+    modeling_nano.causal_conv1d_fn = ops.causal_conv1d_fn
+    modeling_nano.causal_conv1d_update = ops.causal_conv1d_update
+    modeling_nano.mamba_chunk_scan_combined = ops.mamba_chunk_scan_combined
+    modeling_nano.mamba_split_conv1d_scan_combined = ops.mamba_split_conv1d_scan_combined
+    modeling_nano.selective_state_update = ops.selective_state_update
+    modeling_nano.rmsnorm_fn = ops.rmsnorm_fn
+    modeling_nano.is_fast_path_available = True
+    return modeling_nano

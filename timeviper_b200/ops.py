@@ -1,0 +1,263 @@
+"""Reference-facing operators of the Mamba-2 mixer prefill path, backed by hand-written sm_100a CUDA.
+
+Same names, argument meaning and error behaviour as the third-party functions the reference binds at
+timeviper/model/llm/llm_repo/nano/modeling_nano.py:60-82:
+
+  causal_conv1d_fn           causal_conv1d 1.5.2   (call site modeling_nano.py:619-624)
+  mamba_chunk_scan_combined  mamba_ssm 2.2.5       (signature visualize/nano/my_ssd_combined.py:1270-1306,
+                                                    call site modeling_nano.py:639-653)
+  rmsnorm_fn                 mamba_ssm layernorm_gated (call site modeling_nano.py:372-380)
+
+PyTorch is plumbing here: it owns device memory and the stream; every arithmetic step runs in
+libtimeviper_b200.so through the C ABI of include/timeviper_b200.h.  No CPU path exists.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.TV_F32, torch.bfloat16: L.TV_BF16}
+
+
+def _dtype_code(t, what):
+    if t.dtype not in _DT:
+        raise ValueError(f"{what}: dtype {t.dtype} unsupported (float32, bfloat16)")
+    return _DT[t.dtype]
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("timeviper_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------
+def causal_conv1d_fn(x, weight, bias=None, seq_idx=None, initial_states=None, return_final_states=False,
+                     final_states_out=None, activation=None):
+    """x: (batch, dim, seqlen) -- channel-last (x.stride(1) == 1), possibly a strided view;
+    weight: (dim, width); bias: (dim,); initial_states: (batch, dim, width-1);
+    activation: None | "silu" | "swish".  Returns out (batch, dim, seqlen) channel-last
+    [, final_states (batch, dim, width-1)]."""
+    if activation not in (None, "silu", "swish"):
+        raise NotImplementedError("activation must be None, silu, or swish")
+    if seq_idx is not None:
+        raise NotImplementedError("causal_conv1d_fn: seq_idx (packed sequences) is outside the prefill path")
+    if x.dim() != 3:
+        raise ValueError("causal_conv1d_fn: x must be (batch, dim, seqlen)")
+    _require_cuda(x, weight, bias, initial_states)
+    b, dim, seqlen = x.shape
+    if weight.shape[0] != dim or weight.dim() != 2:
+        raise ValueError(f"causal_conv1d_fn: weight {tuple(weight.shape)} does not match dim {dim}")
+    width = weight.shape[1]
+    if x.stride(1) != 1:                       # upstream also accepts channel-first; make it channel-last
+        x = x.transpose(1, 2).contiguous().transpose(1, 2)
+    weight = weight.to(x.dtype).contiguous()
+    bias = None if bias is None else bias.to(x.dtype).contiguous()
+    if initial_states is not None:
+        if tuple(initial_states.shape) != (b, dim, width - 1):
+            raise ValueError("causal_conv1d_fn: initial_states must be (batch, dim, width-1)")
+        initial_states = initial_states.to(x.dtype).contiguous()
+    out = torch.empty((b, seqlen, dim), dtype=x.dtype, device=x.device)
+    fin = None
+    if return_final_states or final_states_out is not None:
+        if final_states_out is not None:
+            if (tuple(final_states_out.shape) != (b, dim, width - 1) or not final_states_out.is_contiguous()
+                    or final_states_out.dtype != x.dtype):
+                raise ValueError("causal_conv1d_fn: final_states_out must be contiguous (batch, dim, width-1)")
+            fin = final_states_out
+        else:
+            fin = torch.empty((b, dim, width - 1), dtype=x.dtype, device=x.device)
+    p = L.ConvParams(x=_ptr(x), weight=_ptr(weight), bias=_ptr(bias), initial_states=_ptr(initial_states),
+                     out=_ptr(out), final_states=_ptr(fin), batch=b, dim=dim, seqlen=seqlen, width=width,
+                     x_batch_stride=x.stride(0), x_seq_stride=x.stride(2),
+                     out_batch_stride=out.stride(0), out_seq_stride=out.stride(1),
+                     silu=int(activation in ("silu", "swish")), dtype=_dtype_code(x, "causal_conv1d_fn"))
+    L.check(L.load().tv_causal_conv1d_fwd(C.byref(p), _stream(x)), "causal_conv1d_fn")
+    out = out.transpose(1, 2)
+    return (out, fin) if return_final_states else out
+
+
+# ------------------------------------------------------------------------------------------------
+def rmsnorm_fn(x, weight, bias, z=None, eps=1e-6, group_size=None, norm_before_gate=True, upcast=True):
+    """Gated grouped RMSNorm: x, z (..., d); weight/bias (d,).  Math is always fp32 (`upcast`)."""
+    _require_cuda(x, weight, bias, z)
+    shape = x.shape
+    d = shape[-1]
+    x2 = x.reshape(-1, d)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    z2 = None
+    if z is not None:
+        if z.shape != shape:
+            raise ValueError("rmsnorm_fn: z must have the shape of x")
+        z2 = z.to(x.dtype).reshape(-1, d)
+        if z2.stride(-1) != 1:
+            z2 = z2.contiguous()
+    if weight.shape != (d,):
+        raise ValueError("rmsnorm_fn: weight must be (d,)")
+    weight = weight.to(x.dtype).contiguous()
+    bias = None if bias is None else bias.to(x.dtype).contiguous()
+    g = d if group_size is None else int(group_size)
+    out = torch.empty((x2.shape[0], d), dtype=x.dtype, device=x.device)
+    if x2.shape[0] == 0:
+        return out.reshape(shape)
+    p = L.RmsnormParams(x=_ptr(x2), z=_ptr(z2), weight=_ptr(weight), bias=_ptr(bias), out=_ptr(out),
+                        rows=x2.shape[0], d=d, group_size=g, x_row_stride=x2.stride(0),
+                        z_row_stride=0 if z2 is None else z2.stride(0), out_row_stride=out.stride(0),
+                        eps=float(eps), norm_before_gate=int(bool(norm_before_gate)),
+                        dtype=_dtype_code(x, "rmsnorm_fn"))
+    L.check(L.load().tv_gated_rmsnorm_fwd(C.byref(p), _stream(x)), "rmsnorm_fn")
+    return out.reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch per (device, stream): the .so never allocates (ownership)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_softplus, dt_limit, mode,
+              force_simt=False, want_final=True, want_logdecay=False):
+    batch, seqlen, nheads, headdim = x.shape
+    ngroups, dstate = B.shape[2], B.shape[3]
+    assert nheads % ngroups == 0
+    assert B.shape == (batch, seqlen, ngroups, dstate)
+    assert dt.shape == (batch, seqlen, nheads)
+    assert A.shape == (nheads,)
+    if C_ is not None:
+        assert C_.shape == B.shape
+    if z is not None:
+        assert z.shape == x.shape
+    if D is not None:
+        assert D.shape == (nheads, headdim) or D.shape == (nheads,)
+    if initial_states is not None:
+        assert initial_states.shape == (batch, nheads, headdim, dstate)
+    _require_cuda(x, dt, A, B, C_, D, z, dt_bias, initial_states)
+    code = _dtype_code(x, "mamba_chunk_scan_combined")
+    dev = x.device
+    # my_ssd_combined.py:775-788: make the last dim contiguous where the kernels need it
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    B = B.to(x.dtype)
+    if B.stride(-1) != 1:
+        B = B.contiguous()
+    if C_ is not None:
+        C_ = C_.to(x.dtype)
+        if C_.stride(-1) != 1:
+            C_ = C_.contiguous()
+    if z is not None:
+        z = z.to(x.dtype)
+        if z.stride(-1) != 1:
+            z = z.contiguous()
+    dt = dt.to(x.dtype)
+    A32 = A.detach().to(torch.float32).contiguous()
+    D32 = None if D is None else D.detach().to(torch.float32).contiguous()
+    bias32 = None if dt_bias is None else dt_bias.detach().to(torch.float32).contiguous()
+    init32 = None if initial_states is None else initial_states.detach().to(torch.float32).contiguous()
+    lo, hi = float(dt_limit[0]), float(dt_limit[1])
+    out = None
+    if mode == L.TV_SSD_FULL:
+        out = torch.empty((batch, seqlen, nheads, headdim), dtype=x.dtype, device=dev)
+    fin = torch.empty((batch, nheads, headdim, dstate), dtype=torch.float32, device=dev) if want_final else None
+    logdecay = torch.empty((batch, nheads), dtype=torch.float32, device=dev) if want_logdecay else None
+    p = L.SsdParams(
+        x=_ptr(x), dt=_ptr(dt), A=_ptr(A32), B=_ptr(B), C=_ptr(C_), D=_ptr(D32), z=_ptr(z),
+        dt_bias=_ptr(bias32), initial_states=_ptr(init32), out=_ptr(out), final_states=_ptr(fin),
+        logdecay_sum=_ptr(logdecay), batch=batch, seqlen=seqlen, nheads=nheads, headdim=headdim,
+        ngroups=ngroups, dstate=dstate, chunk_size=int(chunk_size),
+        x_batch_stride=x.stride(0), x_seq_stride=x.stride(1), x_head_stride=x.stride(2),
+        dt_batch_stride=dt.stride(0), dt_seq_stride=dt.stride(1), dt_head_stride=dt.stride(2),
+        b_batch_stride=B.stride(0), b_seq_stride=B.stride(1), b_group_stride=B.stride(2),
+        c_batch_stride=0 if C_ is None else C_.stride(0), c_seq_stride=0 if C_ is None else C_.stride(1),
+        c_group_stride=0 if C_ is None else C_.stride(2),
+        z_batch_stride=0 if z is None else z.stride(0), z_seq_stride=0 if z is None else z.stride(1),
+        z_head_stride=0 if z is None else z.stride(2),
+        d_has_hdim=int(D is not None and D.dim() == 2), dt_softplus=int(bool(dt_softplus)),
+        dt_min=lo, dt_max=hi if math.isfinite(hi) else float("inf"), dtype=code, mode=mode,
+        force_simt=int(bool(force_simt)))
+    lib = L.load()
+    need = lib.tv_ssd_workspace_bytes(C.byref(p))
+    ws = _workspace(need, dev)
+    L.check(lib.tv_ssd_chunk_scan_fwd(C.byref(p), _ptr(ws), ws.numel(), _stream(x)), "mamba_chunk_scan_combined")
+    return out, fin, logdecay
+
+
+def mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initial_states=None,
+                              seq_idx=None, cu_seqlens=None, dt_softplus=False, dt_limit=(0.0, float("inf")),
+                              return_final_states=False, return_varlen_states=False, _force_simt=False):
+    """
+    Argument:
+        x: (batch, seqlen, nheads, headdim)        dt: (batch, seqlen, nheads)       A: (nheads)
+        B, C: (batch, seqlen, ngroups, dstate)     D: (nheads, headdim) or (nheads,) z: (batch, seqlen, nheads, headdim)
+        dt_bias: (nheads,)                         initial_states: (batch, nheads, headdim, dstate)
+    Return:
+        out: (batch, seqlen, nheads, headdim) [, final_states (batch, nheads, headdim, dstate) fp32]
+    """
+    if seq_idx is not None or cu_seqlens is not None or return_varlen_states:
+        raise NotImplementedError("mamba_chunk_scan_combined: seq_idx / cu_seqlens / varlen states are "
+                                  "outside the prefill path (the reference passes seq_idx=None)")
+    out, fin, _ = _ssd_call(x, dt, A, B, C, chunk_size, D, z, dt_bias, initial_states, dt_softplus, dt_limit,
+                            L.TV_SSD_FULL, force_simt=_force_simt, want_final=return_final_states)
+    return (out, fin) if return_final_states else out
+
+
+def mamba_chunk_state_summary(x, dt, A, B, chunk_size, dt_bias=None, dt_softplus=False,
+                              dt_limit=(0.0, float("inf")), _force_simt=False):
+    """Shard summary for the sequence-sharded path: (final state from a zero initial state (b,H,P,N) fp32,
+    sum over the shard of dt*A (b,H) fp32).  New work -- SURVEY.md section 8e."""
+    _, fin, logdecay = _ssd_call(x, dt, A, B, None, chunk_size, None, None, dt_bias, None, dt_softplus,
+                                 dt_limit, L.TV_SSD_STATE_ONLY, force_simt=_force_simt, want_final=True,
+                                 want_logdecay=True)
+    return fin, logdecay
+
+
+def fold_boundary_states(states, logdecay, rank, initial_states=None):
+    """states (world,b,H,P,N) fp32, logdecay (world,b,H) fp32 -> state entering shard `rank` (b,H,P,N)."""
+    _require_cuda(states, logdecay, initial_states)
+    world, b, H, P, N = states.shape
+    states = states.to(torch.float32).contiguous()
+    logdecay = logdecay.to(torch.float32).contiguous()
+    init = None if initial_states is None else initial_states.to(torch.float32).contiguous()
+    out = torch.empty((b, H, P, N), dtype=torch.float32, device=states.device)
+    L.check(L.load().tv_ssd_fold_boundary_states(_ptr(states), _ptr(logdecay), _ptr(init), _ptr(out), int(rank),
+                                                 b, H, P, N, _stream(states)), "fold_boundary_states")
+    return out
+
+
+def ssd_kernel_family(dtype, headdim, dstate, chunk_size, nheads=128, ngroups=8):
+    """'tcgen05' or 'simt': which kernel family serves this shape (introspection for tests/bench)."""
+    p = L.SsdParams(batch=1, seqlen=chunk_size, nheads=nheads, headdim=headdim, ngroups=ngroups, dstate=dstate,
+                    chunk_size=chunk_size, dtype=_DT[dtype], mode=L.TV_SSD_FULL)
+    return "tcgen05" if L.load().tv_ssd_kernel_family(C.byref(p)) == 1 else "simt"
+
+
+# -- names the reference's fast-path gate needs to be non-None (modeling_nano.py:89-97); decode and training
+#    are outside the prefill path, so they fail loudly instead of silently computing something else --------
+def causal_conv1d_update(*args, **kwargs):
+    raise NotImplementedError("causal_conv1d_update (single-token decode) is outside the prefill path")
+
+
+def selective_state_update(*args, **kwargs):
+    raise NotImplementedError("selective_state_update (single-token decode) is outside the prefill path")
+
+
+def mamba_split_conv1d_scan_combined(*args, **kwargs):
+    raise NotImplementedError("mamba_split_conv1d_scan_combined (training fwd+bwd) is outside the prefill path")
