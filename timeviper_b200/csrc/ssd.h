@@ -13,6 +13,8 @@ struct SimtWorkspace {
 SimtWorkspace simt_workspace_layout(const tv_ssd_params& p);
 int simt_supported(const tv_ssd_params& p);
 int ssd_simt_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s);
+// stage (i): dt activation + per-chunk cumsum into (b, nchunks, H, Q) fp32 arrays (shared by both families)
+int launch_dt_cumsum(const tv_ssd_params& p, float* dt_act, float* cs, cudaStream_t s);
 
 // tcgen05 / TMEM / TMA family (ssd_tc.cu): bf16, P=80, N=128, Q=128
 bool tc_supported(const tv_ssd_params& p);

@@ -326,6 +326,22 @@ int simt_supported(const tv_ssd_params& p) {
   return TV_OK;
 }
 
+int launch_dt_cumsum(const tv_ssd_params& p, float* dt_act, float* cs, cudaStream_t s) {
+  const int Q = p.chunk_size, H = p.nheads, L = p.seqlen;
+  const int nchunks = (int)ceil_div(L, Q);
+  dim3 grid(nchunks, (unsigned)ceil_div(H, 32), p.batch);
+  if (p.dtype == TV_BF16)
+    ssd_dt_cumsum_kernel<__nv_bfloat16><<<grid, 128, Q * 33 * sizeof(float), s>>>(
+        (const __nv_bfloat16*)p.dt, p.A, p.dt_bias, dt_act, cs, L, H, Q, nchunks, p.dt_batch_stride,
+        p.dt_seq_stride, p.dt_head_stride, p.dt_softplus, p.dt_min, p.dt_max);
+  else
+    ssd_dt_cumsum_kernel<float><<<grid, 128, Q * 33 * sizeof(float), s>>>(
+        (const float*)p.dt, p.A, p.dt_bias, dt_act, cs, L, H, Q, nchunks, p.dt_batch_stride, p.dt_seq_stride,
+        p.dt_head_stride, p.dt_softplus, p.dt_min, p.dt_max);
+  TV_CUDA_OK(cudaGetLastError());
+  return TV_OK;
+}
+
 template <typename T, int TP>
 static int run_simt(const tv_ssd_params& p, char* ws, cudaStream_t s) {
   const SimtWorkspace w = simt_workspace_layout(p);
@@ -336,11 +352,8 @@ static int run_simt(const tv_ssd_params& p, char* ws, cudaStream_t s) {
   float* states = (float*)(ws + w.states_off);
   float* CB = (float*)(ws + w.cb_off);
   {
-    dim3 grid(nchunks, (unsigned)ceil_div(H, 32), p.batch);
-    ssd_dt_cumsum_kernel<T><<<grid, 128, Q * 33 * sizeof(float), s>>>(
-        (const T*)p.dt, p.A, p.dt_bias, dt_act, cs, L, H, Q, nchunks, p.dt_batch_stride, p.dt_seq_stride,
-        p.dt_head_stride, p.dt_softplus, p.dt_min, p.dt_max);
-    TV_CUDA_OK(cudaGetLastError());
+    const int rc = launch_dt_cumsum(p, dt_act, cs, s);
+    if (rc != TV_OK) return rc;
   }
   {
     const size_t smem = ((size_t)Q * 16 * TP + (size_t)Q * 128 + Q) * sizeof(float);
