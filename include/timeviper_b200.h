@@ -135,6 +135,10 @@ int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, cons
                                 float* out, int32_t rank, int32_t batch, int32_t nheads,
                                 int32_t headdim, int32_t dstate, void* stream);
 
+/* Debug hook (profiling only): device buffer of nchunks*16 int64 that CTA (0,0) of the fused SSD kernel fills
+ * with clock64() stamps of its pipeline events; NULL (default) disables it. */
+void tv_debug_set_trace(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

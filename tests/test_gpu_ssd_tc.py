@@ -4,7 +4,10 @@ import pytest
 import torch
 
 from oracle import mamba2_ref as R
-from test_gpu_ops import _cpu, _ssd_inputs, relerr
+try:
+    from tests.test_gpu_ops import _cpu, _ssd_inputs, relerr
+except ImportError:  # rootdir-relative collection
+    from test_gpu_ops import _cpu, _ssd_inputs, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-2
@@ -23,7 +26,9 @@ def tv():
 def test_tc_matches_oracle(tv, b, L, H, G):
     x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(b, L, H, 80, G, 128, torch.bfloat16, seed=11)
     init = torch.randn(b, H, 80, 128, device="cuda") * 0.5
-    for kw in (dict(D=D), dict(D=D, z=z, initial_states=init), dict(D=None, dt_limit=(0.01, 0.3))):
+    D2 = torch.randn(H, 80, device="cuda").to(torch.bfloat16)          # (nheads, headdim) skip: explicit D*x path
+    for kw in (dict(D=D), dict(D=D, z=z, initial_states=init), dict(D=None, dt_limit=(0.01, 0.3)), dict(D=D2),
+               dict(D=D2, z=z)):
         out, fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, dt_bias=dt_bias, dt_softplus=True,
                                                 return_final_states=True, **kw)
         torch.cuda.synchronize()

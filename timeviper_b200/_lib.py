@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtimeviper_b200.so")
+LIB_PATH = os.environ.get("TV_LIB_PATH") or os.path.join(HERE, "libtimeviper_b200.so")   # TV_LIB_PATH: tuning builds
 
 TV_F32, TV_BF16 = 0, 1
 TV_SSD_FULL, TV_SSD_STATE_ONLY = 0, 1
@@ -47,7 +47,7 @@ class SsdParams(C.Structure):
 
 EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd",
            "tv_ssd_workspace_bytes", "tv_ssd_chunk_scan_fwd", "tv_ssd_kernel_family",
-           "tv_ssd_fold_boundary_states")
+           "tv_ssd_fold_boundary_states", "tv_debug_set_trace")
 
 _lib = None
 
@@ -76,6 +76,8 @@ def load():
     lib.tv_ssd_fold_boundary_states.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.tv_ssd_fold_boundary_states.restype = C.c_int
+    lib.tv_debug_set_trace.argtypes = [C.c_void_p]
+    lib.tv_debug_set_trace.restype = None
     if lib.tv_abi_version() != 1:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.tv_abi_version()} != 1")
     _lib = lib

@@ -23,8 +23,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// TV_WAIT_MODE (tuning): 0 = plain try_wait spin, 1 = try_wait with a suspend-time hint (TV_WAIT_NS),
+// 2 = plain try_wait + nanosleep(TV_WAIT_NS) after a failed probe (frees issue slots for the working warps)
+#ifndef TV_WAIT_MODE
+#define TV_WAIT_MODE 0
+#endif
+#ifndef TV_WAIT_NS
+#define TV_WAIT_NS 100
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if TV_WAIT_MODE == 1
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TV_WAIT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -32,17 +49,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
-// Bounded spin: a protocol bug must not hang the GPU box (a hang is a strike); trap instead.
+// Bounded spin: a protocol bug must not hang the GPU box (a hang is a strike); report and trap instead.
+__device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  printf("mbar_wait timeout: block (%d,%d) thread %d barrier smem+0x%x parity %u\n", blockIdx.x, blockIdx.y,
+         threadIdx.x, bar_addr, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("mbar_wait timeout: block (%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
+#if TV_WAIT_MODE == 2
+    __nanosleep(TV_WAIT_NS);
+#endif
+    if (++spins > (1u << 22)) mbar_timeout(smem_u32(bar), parity);
   }
 }
 
@@ -80,6 +102,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of one box of a tensor map / of a linear range (no shared memory involved)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+               ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 // 1-D bulk copy global -> shared (bytes multiple of 16, both 16-byte aligned)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -129,6 +159,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 32-byte global store (STG.256, sm_100+)
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 
 // ------------------------------------------------------------------ UMMA descriptors
 enum : uint32_t { SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };

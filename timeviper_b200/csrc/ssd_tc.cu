@@ -17,10 +17,10 @@
 //      y[m,p]    = Yd + exp(cs_m) * Yo + D * x[m,p]   [* silu(z)]         WG_B epilogue -> global
 // Decay, mask and cumsum stay in fp32 registers; only the four contractions touch the tensor cores.
 //
-// Warp roles (320 threads): warps 0-3 = WG_A (builds M), warps 4-7 = WG_B (x scaling, state decay, bf16 state
-// copy, epilogue), warp 8 = TMA producer, warp 9 = MMA issuer + TMEM owner.  Tensor-pipe order per
-// iteration is S(c), G(c+1), O(c), D(c): the state recurrence (the only loop-carried dependency) is issued
-// first, and the look-ahead C.B^T hides the M build and the epilogue of the previous chunk.
+// Warp roles (448 threads): warps 0-3 = WG_A (builds M), warps 4-7 = WG_B (x scaling, state decay, bf16 state
+// copy), warps 8-11 = WG_C (epilogue), warp 12 = TMA producer (+ L2 prefetch 3 chunks ahead), warp 13 = MMA
+// issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers so each is released as soon as
+// its last MMA has been issued.  Tensor-pipe order per iteration is S(c), D(c), G(c+1), O(c).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "ssd.h"
@@ -31,22 +31,22 @@ using namespace sm100;
 
 namespace tc {
 constexpr int Q = 128, P = 80, N = 128;
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;                      // WG_A, WG_B, WG_C (4 warps each) + producer + MMA issuer
 constexpr uint32_t TILE_BC = Q * N * 2;          // 32768: two 16 KB halves (n 0..63 | 64..127), SW128
 constexpr uint32_t TILE_X = 5 * 4096;            // 20480: five 16-wide p atoms, SW32
-constexpr uint32_t OFF_B = 0, OFF_C = TILE_BC, OFF_X = 2 * TILE_BC, OFF_CS = OFF_X + TILE_X, OFF_DT = OFF_CS + 512;
-constexpr uint32_t STAGE = OFF_DT + 512;          // 87040
-constexpr uint32_t OFF_XS = 2 * STAGE, OFF_S = OFF_XS + TILE_X, OFF_F = OFF_S + TILE_X;   // F: 2 x 512 B
+constexpr uint32_t XSTAGE = TILE_X + 1024;       // x tile | cs[128] f32 | dt[128] f32
+constexpr uint32_t OFF_B = 0, OFF_C = 2 * TILE_BC, OFF_X = 4 * TILE_BC;          // two buffers of each
+constexpr uint32_t OFF_XS = OFF_X + 2 * XSTAGE, OFF_S = OFF_XS + TILE_X, OFF_F = OFF_S + TILE_X;   // F: 2 x 512 B
 constexpr uint32_t OFF_D = OFF_F + 1024;          // 80 floats (D row), padded to 512
 constexpr uint32_t OFF_BAR = OFF_D + 512;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + barriers + alignment slack
-static_assert(STAGE % 1024 == 0, "stage must keep 1024-byte alignment");
+static_assert(OFF_XS % 1024 == 0 && OFF_S % 1024 == 0 && XSTAGE % 256 == 0, "tile alignment");
 static_assert(SMEM_BYTES <= kMaxDynSmem, "smem budget");
 // TMEM columns
 constexpr uint32_t T_CB0 = 0, T_CB1 = 128, T_YD = 256, T_YO = 336, T_ST = 416;
 
-enum Bar { FULL0 = 0, FULL1, EMPTY0, EMPTY1, CBFULL0, CBFULL1, MFULL0, MFULL1, XSFULL, SDECAY, SFULL, STDONE,
-           YOFFDONE, YFULL, YEMPTY, NBAR };
+enum Bar { FULLB0 = 0, FULLB1, EMPTYB0, EMPTYB1, FULLC0, FULLC1, EMPTYC0, EMPTYC1, FULLX0, FULLX1, EMPTYX0, EMPTYX1,
+           CBFULL0, CBFULL1, MFULL0, MFULL1, XSFULL, SDECAY, SFULL, STDONE, YOFFDONE, YFULL, YEMPTY, NBAR };
 
 struct Maps { CUtensorMap x, b, c; };
 
@@ -56,37 +56,87 @@ struct Args {
   __nv_bfloat16* out; float* fin; float* logdecay;
   int L, H, G, nchunks, d_has_hdim;
   int64_t zbs, zss, zhs;
+  long long* trace;                                // optional: per-chunk clock64 stamps of CTA (0,0), 16 per chunk
 };
 
+#ifdef TV_ENABLE_TRACE   // profiling builds only (python timeviper_b200/build.py --trace): keeps the hot loops small
+#define TV_TRACE(ev, c)                                                                    \
+  do {                                                                                      \
+    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) a.trace[(int64_t)(c) * 16 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define TV_TRACE(ev, c) do { } while (0)
+#endif
 __device__ __forceinline__ uint32_t off_sw32(int r, int q) {  // row r, 16-byte chunk q (8 p each) of a [128][80] tile
   return (uint32_t)(q >> 1) * 4096u + (uint32_t)r * 32u + (uint32_t)(((q & 1) ^ ((r >> 2) & 1)) << 4);
 }
 }  // namespace tc
 
-template <bool FULL>
+// Tensor-pipe order per iteration c:  S(c)  D(c)  G(c+1)  O(c).
+//   S first: it is the loop-carried dependency (state);  its B tile is released right after it.
+//   D second: M(c) was built during the previous iteration; issuing it early releases the x stage early (x is
+//             the tile with the longest hold time: WG_B needs x(c+2) well before S(c+2)).
+//   G(c+1) third: look-ahead C.B^T; WG_A builds M(c+1) while O(c) and S(c+1) run.
+//   O last: needs the bf16 copy of S_c; releases the C tile and completes y of chunk c.
+// One 32x32 block of M for this warp's 32 rows: M[m,k] = CB[m,k] * 2^(Em + F_k), masked to k <= m on the diagonal
+// block.  Written stage by stage (TMEM load, 32 exponent arguments, 32 MUFU.EX2, 32 FMUL, 16 packs, TMEM store) so
+// that the exp2 stream is issue-bound on the XU pipe (8 cycles per warp instruction) instead of latency-bound.
+template <bool DFOLD>
+__device__ __forceinline__ void m_block(uint32_t t_src, uint32_t t_dst, const float* __restrict__ sFk, float Em,
+                                        int lane, float Dh, bool diag) {
+  uint32_t r[32];
+  tmem_ld32(t_src, r);
+  float e[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 f4 = *reinterpret_cast<const float4*>(sFk + j);
+    e[j] = Em + f4.x; e[j + 1] = Em + f4.y; e[j + 2] = Em + f4.z; e[j + 3] = Em + f4.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) e[j] = ex2_approx(e[j]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    e[j] *= __uint_as_float(r[j]);
+    if (diag && j > lane) e[j] = 0.f;                   // causal mask (diagonal block only)
+    if (DFOLD && diag && j == lane) e[j] += Dh;         // D skip folded into the diagonal
+  }
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+  tmem_st16(t_dst, pk);
+}
+
+// DFOLD: D is a per-head scalar and is added to the diagonal of M (bf16 A operand), so that Yd = (M + D I) x and
+// the epilogue never touches x.  For bf16 parameters D*x is exact in the fp32 accumulator; the only extra rounding
+// is bf16(M_mm + D), of the order of the bf16 rounding of y itself.  D of shape (H, P) takes the explicit path.
+template <bool FULL, bool HAS_Z, bool DFOLD>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   using namespace tc;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBAR * 8);
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
-  const int g = h / (a.H / a.G);
+  const int hpg = a.H / a.G;
+  const int g = h / hpg;
   const int n = a.nchunks;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[FULL0], 1); mbar_init(&bars[FULL1], 1);
-    mbar_init(&bars[EMPTY0], FULL ? 257 : 129); mbar_init(&bars[EMPTY1], FULL ? 257 : 129);
-    mbar_init(&bars[CBFULL0], 1); mbar_init(&bars[CBFULL1], 1);
-    mbar_init(&bars[MFULL0], 128); mbar_init(&bars[MFULL1], 128);
-    mbar_init(&bars[XSFULL], 128); mbar_init(&bars[SDECAY], 128); mbar_init(&bars[SFULL], 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[FULLB0 + i], 1); mbar_init(&bars[FULLC0 + i], 1); mbar_init(&bars[FULLX0 + i], 1);
+      mbar_init(&bars[EMPTYB0 + i], 1); mbar_init(&bars[EMPTYC0 + i], 1);
+      mbar_init(&bars[EMPTYX0 + i], FULL ? (DFOLD ? 9 : 13) : 4);   // one lane per consumer warp + the D(c) commit
+      mbar_init(&bars[CBFULL0 + i], 1); mbar_init(&bars[MFULL0 + i], 4);
+    }
+    mbar_init(&bars[XSFULL], 4); mbar_init(&bars[SDECAY], 4); mbar_init(&bars[SFULL], 4);
     mbar_init(&bars[STDONE], 1); mbar_init(&bars[YOFFDONE], 1); mbar_init(&bars[YFULL], 1);
-    mbar_init(&bars[YEMPTY], 128);
+    mbar_init(&bars[YEMPTY], 4);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 13) tmem_alloc<512>(tmem_slot);
   if (threadIdx.x < P) {
     float* sD = reinterpret_cast<float*>(smem + OFF_D);
     sD[threadIdx.x] = a.D == nullptr ? 0.f : (a.d_has_hdim ? a.D[h * P + threadIdx.x] : a.D[h]);
@@ -97,253 +147,249 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   const uint32_t tmem = *tmem_slot;
   const int64_t row0 = ((int64_t)b * n) * a.H + h;     // (b, c, h) row of dt_act / cs is row0 + c*H
 
-  if (warp == 8) {
+  if (warp == 12) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       prefetch_tmap(&maps.x); prefetch_tmap(&maps.b);
       if (FULL) prefetch_tmap(&maps.c);
-      for (int c = 0; c < n; ++c) {
-        const int s = c & 1;
-        uint8_t* st = smem + s * STAGE;
-        if (c >= 2) mbar_wait(&bars[EMPTY0 + s], ((c >> 1) - 1) & 1);
-        mbar_arrive_expect_tx(&bars[FULL0 + s], (FULL ? 2 * TILE_BC : TILE_BC) + TILE_X + 1024);
+      const bool group_leader = (h % hpg) == 0;      // one CTA per group warms L2 with the shared B / C tiles
+      auto l2_prefetch = [&](int c) {
         const int t0 = c * Q;
-        tma_load_4d(st + OFF_B, &maps.b, &bars[FULL0 + s], 0, g, t0, b);
-        tma_load_4d(st + OFF_B + 16384, &maps.b, &bars[FULL0 + s], 64, g, t0, b);
-        if (FULL) {
-          tma_load_4d(st + OFF_C, &maps.c, &bars[FULL0 + s], 0, g, t0, b);
-          tma_load_4d(st + OFF_C + 16384, &maps.c, &bars[FULL0 + s], 64, g, t0, b);
-        }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) tma_load_4d(st + OFF_X + i * 4096, &maps.x, &bars[FULL0 + s], 16 * i, h, t0, b);
-        bulk_load(st + OFF_CS, a.cs + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULL0 + s]);
-        bulk_load(st + OFF_DT, a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULL0 + s]);
+        for (int i = 0; i < 5; ++i) tma_prefetch_4d(&maps.x, 16 * i, h, t0, b);
+        bulk_prefetch(a.cs + (row0 + (int64_t)c * a.H) * Q, 512);
+        bulk_prefetch(a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512);
+        if (group_leader) {
+          tma_prefetch_4d(&maps.b, 0, g, t0, b); tma_prefetch_4d(&maps.b, 64, g, t0, b);
+          if (FULL) { tma_prefetch_4d(&maps.c, 0, g, t0, b); tma_prefetch_4d(&maps.c, 64, g, t0, b); }
+        }
+      };
+      constexpr int PF = 3;                         // L2 prefetch distance (chunks ahead of the smem loads)
+      for (int c = 1; c < PF && c < n; ++c) l2_prefetch(c);
+      for (int c = 0; c < n; ++c) {
+        const int s = c & 1, u = c >> 1;
+        const int t0 = c * Q;
+        if (c + PF < n) l2_prefetch(c + PF);
+        if (c >= 2) mbar_wait(&bars[EMPTYB0 + s], (u - 1) & 1);
+        TV_TRACE(0, c);
+#ifdef TV_ENABLE_TRACE
+        if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          a.trace[(int64_t)c * 16 + 15] = (long long)gt;
+        }
+#endif
+        mbar_arrive_expect_tx(&bars[FULLB0 + s], TILE_BC);
+        tma_load_4d(smem + OFF_B + s * TILE_BC, &maps.b, &bars[FULLB0 + s], 0, g, t0, b);
+        tma_load_4d(smem + OFF_B + s * TILE_BC + 16384, &maps.b, &bars[FULLB0 + s], 64, g, t0, b);
+        if (FULL) {
+          if (c >= 2) mbar_wait(&bars[EMPTYC0 + s], (u - 1) & 1);
+          mbar_arrive_expect_tx(&bars[FULLC0 + s], TILE_BC);
+          tma_load_4d(smem + OFF_C + s * TILE_BC, &maps.c, &bars[FULLC0 + s], 0, g, t0, b);
+          tma_load_4d(smem + OFF_C + s * TILE_BC + 16384, &maps.c, &bars[FULLC0 + s], 64, g, t0, b);
+        }
+        if (c >= 2) mbar_wait(&bars[EMPTYX0 + s], (u - 1) & 1);
+        TV_TRACE(14, c);
+        uint8_t* xs_ = smem + OFF_X + s * XSTAGE;
+        mbar_arrive_expect_tx(&bars[FULLX0 + s], XSTAGE);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) tma_load_4d(xs_ + i * 4096, &maps.x, &bars[FULLX0 + s], 16 * i, h, t0, b);
+        bulk_load(xs_ + TILE_X, a.cs + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULLX0 + s]);
+        bulk_load(xs_ + TILE_X + 512, a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULLX0 + s]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
       constexpr uint32_t ID_CB = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t ID_Y = umma_idesc_bf16(128, P, false, true);
       constexpr uint32_t ID_ST = umma_idesc_bf16(128, P, true, true);
       const uint32_t sbase = smem_u32(smem);
+      // descriptor templates; per-MMA offsets are added to the 14-bit start-address field (units of 16 bytes)
+      const uint64_t dB_k = umma_smem_desc(sbase + OFF_B, 16, 1024, SWZ_128B);        // B as K-major operand (G)
+      const uint64_t dB_mn = umma_smem_desc(sbase + OFF_B, 16384, 1024, SWZ_128B);    // B as MN-major A operand (S)
+      const uint64_t dC_k = umma_smem_desc(sbase + OFF_C, 16, 1024, SWZ_128B);
+      const uint64_t dX = umma_smem_desc(sbase + OFF_X, 4096, 256, SWZ_32B);
+      const uint64_t dXS = umma_smem_desc(sbase + OFF_XS, 4096, 256, SWZ_32B);
+      const uint64_t dS = umma_smem_desc(sbase + OFF_S, 4096, 256, SWZ_32B);
       auto issue_cb = [&](int c) {   // G(c): CB = C . B^T
-        const int s = c & 1;
-        mbar_wait(&bars[FULL0 + s], (c >> 1) & 1);
+        const int s = c & 1, u = c >> 1;
+        mbar_wait(&bars[FULLB0 + s], u & 1);
+        mbar_wait(&bars[FULLC0 + s], u & 1);
         tc_fence_after();
-        const uint32_t sc = sbase + s * STAGE + OFF_C, sb = sbase + s * STAGE + OFF_B;
+        TV_TRACE(1, c);
+        const uint64_t so = (uint64_t)(s * (TILE_BC >> 4));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t o = (j >> 2) * 16384 + (j & 3) * 32;
-          umma_ss(tmem + (s ? T_CB1 : T_CB0), umma_smem_desc(sc + o, 16, 1024, SWZ_128B),
-                  umma_smem_desc(sb + o, 16, 1024, SWZ_128B), ID_CB, j > 0);
+          const uint64_t o = so + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
+          umma_ss(tmem + (s ? T_CB1 : T_CB0), dC_k + o, dB_k + o, ID_CB, j > 0);
         }
         umma_commit(&bars[CBFULL0 + s]);
       };
       if (FULL) issue_cb(0);
       for (int c = 0; c < n; ++c) {
-        const int s = c & 1;
-        const uint32_t st = sbase + s * STAGE;
+        const int s = c & 1, u = c >> 1;
         // ---- S(c): state += B^T . xs
-        mbar_wait(&bars[FULL0 + s], (c >> 1) & 1);
+        mbar_wait(&bars[FULLB0 + s], u & 1);
         mbar_wait(&bars[SDECAY], c & 1);
         mbar_wait(&bars[XSFULL], c & 1);
         tc_fence_after();
+        TV_TRACE(2, c);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          umma_ss(tmem + T_ST, umma_smem_desc(st + OFF_B + j * 2048, 16384, 1024, SWZ_128B),
-                  umma_smem_desc(sbase + OFF_XS + j * 512, 4096, 256, SWZ_32B), ID_ST, 1u);
+          umma_ss(tmem + T_ST, dB_mn + (uint64_t)(s * (TILE_BC >> 4) + j * 128), dXS + (uint64_t)(j * 32), ID_ST, 1u);
         umma_commit(&bars[STDONE]);
+        umma_commit(&bars[EMPTYB0 + s]);
         if (FULL) {
+          // ---- D(c): Yd = M . x   (A = M, packed bf16 in the first 64 columns of this chunk's CB buffer)
+          mbar_wait(&bars[FULLX0 + s], u & 1);
+          mbar_wait(&bars[MFULL0 + s], u & 1);
+          if (c > 0) mbar_wait(&bars[YEMPTY], (c - 1) & 1);
+          tc_fence_after();
+          TV_TRACE(4, c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_ts(tmem + T_YD, tmem + (s ? T_CB1 : T_CB0) + j * 8,
+                    dX + (uint64_t)(s * (XSTAGE >> 4) + j * 32), ID_Y, j > 0);
+          umma_commit(&bars[EMPTYX0 + s]);
           // ---- G(c+1)
           if (c + 1 < n) issue_cb(c + 1);
           // ---- O(c): Yo = C . S_c
           mbar_wait(&bars[SFULL], c & 1);
-          if (c > 0) mbar_wait(&bars[YEMPTY], (c - 1) & 1);
           tc_fence_after();
+          TV_TRACE(3, c);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t o = (j >> 2) * 16384 + (j & 3) * 32;
-            umma_ss(tmem + T_YO, umma_smem_desc(st + OFF_C + o, 16, 1024, SWZ_128B),
-                    umma_smem_desc(sbase + OFF_S + j * 512, 4096, 256, SWZ_32B), ID_Y, j > 0);
+            const uint64_t o = (uint64_t)(s * (TILE_BC >> 4)) + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
+            umma_ss(tmem + T_YO, dC_k + o, dS + (uint64_t)(j * 32), ID_Y, j > 0);
           }
           umma_commit(&bars[YOFFDONE]);
-          // ---- D(c): Yd = M . x   (A = M, packed bf16 in the first 64 columns of this chunk's CB buffer)
-          mbar_wait(&bars[MFULL0 + s], (c >> 1) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_ts(tmem + T_YD, tmem + (s ? T_CB1 : T_CB0) + j * 8,
-                    umma_smem_desc(st + OFF_X + j * 512, 4096, 256, SWZ_32B), ID_Y, j > 0);
           umma_commit(&bars[YFULL]);
+          umma_commit(&bars[EMPTYC0 + s]);
         }
-        umma_commit(&bars[EMPTY0 + s]);   // every MMA that reads stage s has been issued
       }
     }
   } else if (warp < 4) {
     // =========================== WG_A: M = CB (.) decay, in place in TMEM ===========================
     if (FULL) {
-      const int m = threadIdx.x;
+      const int m = threadIdx.x, lane = threadIdx.x & 31;
       const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
       constexpr float LOG2E = 1.4426950408889634f;
+      const float Dh = (DFOLD && a.D != nullptr) ? a.D[h] : 0.f;
       for (int c = 0; c < n; ++c) {
-        const int s = c & 1;
-        const float* sCS = reinterpret_cast<const float*>(smem + s * STAGE + OFF_CS);
-        const float* sDT = reinterpret_cast<const float*>(smem + s * STAGE + OFF_DT);
+        const int s = c & 1, u = c >> 1;
+        const float* sCS = reinterpret_cast<const float*>(smem + OFF_X + s * XSTAGE + TILE_X);
+        const float* sDT = sCS + 128;
         float* sF = reinterpret_cast<float*>(smem + OFF_F + s * 512);
-        mbar_wait(&bars[FULL0 + s], (c >> 1) & 1);
+        mbar_wait(&bars[FULLX0 + s], u & 1);
         const float Em = sCS[m] * LOG2E;
         sF[m] = __log2f(sDT[m]) - Em;            // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
         named_bar_sync(1, 128);
-        mbar_arrive(&bars[EMPTY0 + s]);          // cs/dt of this stage are consumed (F lives in its own buffer)
-        mbar_wait(&bars[CBFULL0 + s], (c >> 1) & 1);
+        if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);   // cs/dt consumed by this warp (F lives in its own buffer)
+        mbar_wait(&bars[CBFULL0 + s], u & 1);
         tc_fence_after();
+        if (threadIdx.x == 0) TV_TRACE(5, c);
+        if (threadIdx.x == 96) TV_TRACE(16 * n + 0, c);
         const uint32_t tcb = tmem + (s ? T_CB1 : T_CB0) + lane_base;
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          uint32_t pk[16];
-          if (kb > warp) {                       // whole 32x32 block above the diagonal
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {         // rolled on purpose: one copy of the block body in the I-cache
+          if (kb > warp) {                       // whole 32x32 block above the diagonal: M = 0
+            uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            tmem_st16(tcb + kb * 16, pk);
           } else {
-            uint32_t r[32];
-            tmem_ld32(tcb + kb * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 f4 = *reinterpret_cast<const float4*>(sF + kb * 32 + j);
-              const float f[4] = {f4.x, f4.y, f4.z, f4.w};
-              float v[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int k = kb * 32 + j + i;
-                const float e = exp2f(Em + f[i]);
-                v[i] = (k <= m) ? __uint_as_float(r[j + i]) * e : 0.f;
-              }
-              pk[(j >> 1)] = pack_bf16x2(v[0], v[1]);
-              pk[(j >> 1) + 1] = pack_bf16x2(v[2], v[3]);
-            }
+            m_block<DFOLD>(tcb + kb * 32, tcb + kb * 16, sF + kb * 32, Em, lane, Dh, kb == warp);
           }
-          tmem_st16(tcb + kb * 16, pk);
         }
         tmem_st_wait();
+        if (threadIdx.x == 96) TV_TRACE(16 * n + 13, c);
         tc_fence_before();
-        mbar_arrive(&bars[MFULL0 + s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[MFULL0 + s]);
+        if (threadIdx.x == 0) TV_TRACE(6, c);
       }
     }
-  } else {
-    // =========================== WG_B: xs, state decay / bf16 copy, epilogue ===========================
-    const int r = threadIdx.x - 128;             // token row (x, y) and state row n
+  } else if (warp < 8) {
+    // =========================== WG_B: xs = w.x, state decay and bf16 state copy ===========================
+    const int r = threadIdx.x - 128, lane = threadIdx.x & 31;   // token row of x / state row n
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const float* sD = reinterpret_cast<const float*>(smem + OFF_D);
-    uint32_t xkeep[40];                           // x row of the previous chunk (bf16x2), for D*x in its epilogue
-    float e_keep = 0.f;
     float logsum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 40; ++i) xkeep[i] = 0u;
-
-    auto epilogue = [&](int c) {                  // y rows of chunk c
-      mbar_wait(&bars[YFULL], c & 1);
-      tc_fence_after();
-      uint32_t yo_pk[40];
-      const int t = c * Q + r;
-#pragma unroll
-      for (int pc = 0; pc < 5; ++pc) {
-        uint32_t yd[16], yo[16];
-        tmem_ld16(tmem + T_YD + lane_base + pc * 16, yd);
-        tmem_ld16(tmem + T_YO + lane_base + pc * 16, yo);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const uint32_t xp = xkeep[pc * 8 + (j >> 1)];
-          const float x0 = __uint_as_float(xp << 16), x1 = __uint_as_float(xp & 0xffff0000u);
-          float y0 = fmaf(e_keep, __uint_as_float(yo[j]), __uint_as_float(yd[j]));
-          float y1 = fmaf(e_keep, __uint_as_float(yo[j + 1]), __uint_as_float(yd[j + 1]));
-          y0 = fmaf(sD[pc * 16 + j], x0, y0);
-          y1 = fmaf(sD[pc * 16 + j + 1], x1, y1);
-          if (a.z != nullptr && t < a.L) {
-            const __nv_bfloat16* zp = a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs + pc * 16 + j;
-            y0 *= silu<true>(__bfloat162float(zp[0]));
-            y1 *= silu<true>(__bfloat162float(zp[1]));
-          }
-          yo_pk[pc * 8 + (j >> 1)] = pack_bf16x2(y0, y1);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&bars[YEMPTY]);                 // Yd / Yo may be overwritten
-      if (t < a.L) {
-        uint4* op = reinterpret_cast<uint4*>(a.out + (((int64_t)b * a.L + t) * a.H + h) * P);
-#pragma unroll
-        for (int q = 0; q < 10; ++q) op[q] = make_uint4(yo_pk[4 * q], yo_pk[4 * q + 1], yo_pk[4 * q + 2], yo_pk[4 * q + 3]);
-      }
-    };
-
     for (int c = 0; c < n; ++c) {
-      const int s = c & 1;
-      const uint8_t* st = smem + s * STAGE;
-      const float* sCS = reinterpret_cast<const float*>(st + OFF_CS);
-      const float* sDT = reinterpret_cast<const float*>(st + OFF_DT);
-      mbar_wait(&bars[FULL0 + s], (c >> 1) & 1);
-      const float cs_last = sCS[Q - 1], cs_r = sCS[r];
-      const float w_r = sDT[r] * __expf(cs_last - cs_r);
-      const float e_r = __expf(cs_r), a_c = __expf(cs_last);
+      const int s = c & 1, u = c >> 1;
+      const uint8_t* xst = smem + OFF_X + s * XSTAGE;
+      const float* sCS = reinterpret_cast<const float*>(xst + TILE_X);
+      const float* sDT = sCS + 128;
+      mbar_wait(&bars[FULLX0 + s], u & 1);
+      if (r == 0) TV_TRACE(7, c);
+      const float cs_last = sCS[Q - 1];
+      const float w_r = sDT[r] * __expf(cs_last - sCS[r]);
+      const float a_c = __expf(cs_last);
       logsum += cs_last;
-      // ---- x row -> registers; xs = x * w_r
-      uint32_t xcur[40], xs[40];
+      const __nv_bfloat162 w2 = __float2bfloat162_rn(w_r);
+      uint32_t xs[40];
 #pragma unroll
       for (int q = 0; q < 10; ++q) {
-        const uint4 v = *reinterpret_cast<const uint4*>(st + OFF_X + off_sw32(r, q));
-        xcur[4 * q] = v.x; xcur[4 * q + 1] = v.y; xcur[4 * q + 2] = v.z; xcur[4 * q + 3] = v.w;
-      }
-      mbar_arrive(&bars[EMPTY0 + s]);             // smem of this stage consumed by WG_B
+        uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, q));
+        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
-      for (int i = 0; i < 40; ++i)
-        xs[i] = pack_bf16x2(__uint_as_float(xcur[i] << 16) * w_r, __uint_as_float(xcur[i] & 0xffff0000u) * w_r);
-      // ---- previous state MMA done: xs buffer is free and S_c (entering state) is complete in TMEM
+        for (int i = 0; i < 4; ++i) hv[i] = __hmul2(hv[i], w2);
+        xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);
+      // ---- previous state MMA done: the xs buffer is free and S_c (entering state) is complete in TMEM
       if (c > 0) { mbar_wait(&bars[STDONE], (c - 1) & 1); tc_fence_after(); }
+      if (r == 0) TV_TRACE(8, c);
 #pragma unroll
       for (int q = 0; q < 10; ++q)
         *reinterpret_cast<uint4*>(smem + OFF_XS + off_sw32(r, q)) = make_uint4(xs[4 * q], xs[4 * q + 1], xs[4 * q + 2], xs[4 * q + 3]);
       fence_proxy_async();
-      mbar_arrive(&bars[XSFULL]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[XSFULL]);
       // ---- state row n = r: decay in place (critical path), keep a bf16 copy of the un-decayed entering state
       uint32_t spk[40];
 #pragma unroll
-      for (int pc = 0; pc < 5; ++pc) {
-        uint32_t v[16];
+      for (int half = 0; half < 2; ++half) {       // 48 + 32 columns: bounds registers, two TMEM round trips
+        const int c0 = half * 48, nc = half ? 2 : 3;
+        uint32_t v[48];
         if (c == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = a.init == nullptr ? 0u
-                                     : __float_as_uint(a.init[(((int64_t)b * a.H + h) * P + pc * 16 + j) * N + r]);
+          for (int j = 0; j < 48; ++j)
+            if (j < nc * 16)
+              v[j] = a.init == nullptr ? 0u : __float_as_uint(a.init[(((int64_t)b * a.H + h) * P + c0 + j) * N + r]);
         } else {
-          tmem_ld16(tmem + T_ST + lane_base + pc * 16, v);
+#pragma unroll
+          for (int pc = 0; pc < 3; ++pc)
+            if (pc < nc) tmem_ld16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
           tmem_ld_wait();
         }
 #pragma unroll
-        for (int j = 0; j < 16; j += 2)
-          spk[pc * 8 + (j >> 1)] = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+        for (int j = 0; j < 48; j += 2)
+          if (j < nc * 16) spk[(c0 + j) >> 1] = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * a_c);
-        tmem_st16(tmem + T_ST + lane_base + pc * 16, v);
+        for (int j = 0; j < 48; ++j)
+          if (j < nc * 16) v[j] = __float_as_uint(__uint_as_float(v[j]) * a_c);
+#pragma unroll
+        for (int pc = 0; pc < 3; ++pc)
+          if (pc < nc) tmem_st16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bars[SDECAY]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[SDECAY]);
+      if (r == 0) TV_TRACE(9, c);
       if (FULL) {
         if (c > 0) mbar_wait(&bars[YOFFDONE], (c - 1) & 1);    // O(c-1) finished reading the bf16 state copy
 #pragma unroll
         for (int q = 0; q < 10; ++q)
           *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, q)) = make_uint4(spk[4 * q], spk[4 * q + 1], spk[4 * q + 2], spk[4 * q + 3]);
         fence_proxy_async();
-        mbar_arrive(&bars[SFULL]);
-        if (c > 0) epilogue(c - 1);
-#pragma unroll
-        for (int i = 0; i < 40; ++i) xkeep[i] = xcur[i];
-        e_keep = e_r;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[SFULL]);
+        if (r == 0) TV_TRACE(10, c);
       }
     }
-    if (FULL) epilogue(n - 1);
     // ---- final state = state after the last chunk
     mbar_wait(&bars[STDONE], (n - 1) & 1);
     tc_fence_after();
@@ -359,18 +405,102 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       }
     }
     if (a.logdecay != nullptr && r == 0) a.logdecay[(int64_t)b * a.H + h] = logsum;
+  } else if (warp < 12) {
+    // =========================== WG_C: epilogue  y = Yd + exp(cs_m) Yo + D x  [* silu(z)] ===========================
+    if (FULL) {
+      const int r = threadIdx.x - 256, lane = threadIdx.x & 31;   // token row m
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      const float* sD = reinterpret_cast<const float*>(smem + OFF_D);
+      for (int c = 0; c < n; ++c) {
+        const int s = c & 1, u = c >> 1;
+        const uint8_t* xst = smem + OFF_X + s * XSTAGE;
+        const int t = c * Q + r;
+        float yv[80];                                // D * x (explicit path) or 0; then accumulates Yd + exp(cs_m) * Yo
+        float e_r;
+        if (!DFOLD) {
+          mbar_wait(&bars[FULLX0 + s], u & 1);
+          e_r = __expf(reinterpret_cast<const float*>(xst + TILE_X)[r]);
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, q));
+            const float4 da = *reinterpret_cast<const float4*>(sD + 8 * q), db = *reinterpret_cast<const float4*>(sD + 8 * q + 4);
+            yv[8 * q + 0] = da.x * __uint_as_float(v.x << 16); yv[8 * q + 1] = da.y * __uint_as_float(v.x & 0xffff0000u);
+            yv[8 * q + 2] = da.z * __uint_as_float(v.y << 16); yv[8 * q + 3] = da.w * __uint_as_float(v.y & 0xffff0000u);
+            yv[8 * q + 4] = db.x * __uint_as_float(v.z << 16); yv[8 * q + 5] = db.y * __uint_as_float(v.z & 0xffff0000u);
+            yv[8 * q + 6] = db.z * __uint_as_float(v.w << 16); yv[8 * q + 7] = db.w * __uint_as_float(v.w & 0xffff0000u);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);
+        } else {
+          e_r = __expf(a.cs[(row0 + (int64_t)c * a.H) * Q + r]);   // one coalesced 512-byte row per chunk (L2 hit)
+        }
+        uint32_t zk[HAS_Z ? 40 : 1];
+        if (HAS_Z) {
+          if (t < a.L) {
+            const uint4* zp = reinterpret_cast<const uint4*>(a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs);
+#pragma unroll
+            for (int q = 0; q < 10; ++q) {
+              const uint4 v = zp[q];
+              zk[(4 * q) % (HAS_Z ? 40 : 1)] = v.x; zk[(4 * q + 1) % (HAS_Z ? 40 : 1)] = v.y;
+              zk[(4 * q + 2) % (HAS_Z ? 40 : 1)] = v.z; zk[(4 * q + 3) % (HAS_Z ? 40 : 1)] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < (HAS_Z ? 40 : 1); ++i) zk[i] = 0u;
+          }
+        }
+        mbar_wait(&bars[YFULL], c & 1);
+        tc_fence_after();
+        if (r == 0) TV_TRACE(11, c);
+#pragma unroll
+        for (int pc = 0; pc < 5; ++pc) {
+          uint32_t yd[16], yo[16];
+          tmem_ld16(tmem + T_YD + lane_base + pc * 16, yd);
+          tmem_ld16(tmem + T_YO + lane_base + pc * 16, yo);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            yv[pc * 16 + j] = DFOLD ? fmaf(e_r, __uint_as_float(yo[j]), __uint_as_float(yd[j]))
+                                    : yv[pc * 16 + j] + fmaf(e_r, __uint_as_float(yo[j]), __uint_as_float(yd[j]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[YEMPTY]);   // Yd / Yo may be overwritten
+        if (r == 0) TV_TRACE(12, c);
+        uint32_t ypk[40];
+#pragma unroll
+        for (int j = 0; j < 80; j += 2) {
+          float y0 = yv[j], y1 = yv[j + 1];
+          if (HAS_Z) {
+            const uint32_t zp2 = zk[(j >> 1) % (HAS_Z ? 40 : 1)];
+            y0 *= silu<true>(__uint_as_float(zp2 << 16));
+            y1 *= silu<true>(__uint_as_float(zp2 & 0xffff0000u));
+          }
+          ypk[j >> 1] = pack_bf16x2(y0, y1);
+        }
+        if (t < a.L) {
+          __nv_bfloat16* op = a.out + (((int64_t)b * a.L + t) * a.H + h) * P;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) st_global_v8(op + 16 * q, &ypk[8 * q]);
+        }
+        if (r == 0) TV_TRACE(13, c);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == 13) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------ host
+static void* g_trace_ptr = nullptr;   // debug: device buffer of nchunks*16 int64 (tv_debug_set_trace)
+void set_trace_buffer(void* p) { g_trace_ptr = p; }
 bool tc_supported(const tv_ssd_params& p) {
   if (p.dtype != TV_BF16 || p.headdim != tc::P || p.dstate != tc::N || p.chunk_size != tc::Q) return false;
   if (p.nheads % p.ngroups != 0) return false;
   auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
-  if (!al16(p.x) || !al16(p.B) || (p.mode == TV_SSD_FULL && (!al16(p.C) || !al16(p.out)))) return false;
+  if (!al16(p.x) || !al16(p.B) || (p.mode == TV_SSD_FULL && (!al16(p.C) || ((uintptr_t)p.out & 31) != 0))) return false;
+  if (p.z != nullptr && (!al16(p.z) || p.z_head_stride % 8 || p.z_seq_stride % 8 || p.z_batch_stride % 8)) return false;
   auto m8 = [](int64_t v) { return v % 8 == 0; };
   if (!m8(p.x_head_stride) || !m8(p.x_seq_stride) || !m8(p.x_batch_stride) || !m8(p.b_group_stride) ||
       !m8(p.b_seq_stride) || !m8(p.b_batch_stride))
@@ -431,15 +561,20 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
   a.dt_act = dt_act; a.cs = cs; a.D = p.D; a.z = (const __nv_bfloat16*)p.z; a.init = p.initial_states;
   a.out = (__nv_bfloat16*)p.out; a.fin = p.final_states; a.logdecay = p.logdecay_sum;
   a.L = p.seqlen; a.H = p.nheads; a.G = p.ngroups; a.nchunks = nchunks; a.d_has_hdim = p.d_has_hdim;
+  a.trace = (long long*)g_trace_ptr;
   a.zbs = p.z_batch_stride; a.zss = p.z_seq_stride; a.zhs = p.z_head_stride;
   dim3 grid(p.nheads, p.batch);
-  if (p.mode == TV_SSD_FULL) {
-    TV_CUDA_OK(cudaFuncSetAttribute(ssd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    ssd_fused_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(maps, a);
-  } else {
-    TV_CUDA_OK(cudaFuncSetAttribute(ssd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    ssd_fused_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(maps, a);
-  }
+  auto launch = [&](auto kern) -> int {
+    TV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    kern<<<grid, THREADS, SMEM_BYTES, s>>>(maps, a);
+    return TV_OK;
+  };
+  int lrc;
+  const bool dfold = !p.d_has_hdim;          // scalar-per-head D (or no D): fold into M's diagonal
+  if (p.mode != TV_SSD_FULL) lrc = launch(ssd_fused_kernel<false, false, true>);
+  else if (p.z != nullptr) lrc = dfold ? launch(ssd_fused_kernel<true, true, true>) : launch(ssd_fused_kernel<true, true, false>);
+  else lrc = dfold ? launch(ssd_fused_kernel<true, false, true>) : launch(ssd_fused_kernel<true, false, false>);
+  if (lrc != TV_OK) return lrc;
   TV_CUDA_OK(cudaGetLastError());
   return TV_OK;
 }
