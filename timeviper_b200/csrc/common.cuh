@@ -57,6 +57,19 @@ template <> __device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfl
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+// raw 16-byte register image -> N floats
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& r, float (&v)[Vec16<T>::N]);
+template <> __device__ __forceinline__ void unpack16<float>(const uint4& r, float (&v)[4]) {
+  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+}
+template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
 template <typename T> __device__ __forceinline__ void store16(T* p, const float (&v)[Vec16<T>::N]);
 template <> __device__ __forceinline__ void store16<float>(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

@@ -6,19 +6,29 @@
 // arbitrary batch/row strides and only requires unit channel stride and 16-byte alignment.
 //
 // Roofline: pure HBM streaming, 2 * dim * sizeof(T) bytes per token (49,152 B at dim 12288, bf16).
-// Layout/tiling: one thread owns 16 bytes of channels (8 bf16) and walks TOK consecutive tokens with the
-// K-1 previous rows kept in registers, so every x element is read once per CTA (halo re-read = (K-1)/TOK,
-// served from L2); a warp reads/writes 512 contiguous bytes per token row.
+// Layout/tiling: one thread owns 16 bytes of channels (8 bf16 / 4 fp32) and walks TOK consecutive tokens with the
+// K-1 previous rows kept in registers, so every x element is read once per CTA (halo re-read = (K-1)/TOK, served
+// from L2); a warp reads/writes 512 contiguous bytes per token row.
 #include "common.cuh"
 
 namespace tv {
 
 constexpr int CONV_THREADS = 128;
 constexpr int CONV_TOK = 64;   // tokens per CTA along the sequence
-constexpr int CONV_U = 4;      // independent 16-byte loads in flight per thread
+// channels per thread = one 16-byte access: 8 (bf16) / 4 (fp32); a warp covers 512 contiguous bytes per token row
+constexpr int CONV_U = 8;      // independent row loads in flight per thread (kept as raw words until used)
 
+template <typename T> struct Raw4 {   // register image of one 16-byte access
+  uint4 r;
+  __device__ __forceinline__ void load(const T* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[Vec16<T>::N]) const { unpack16<T>(r, v); }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[Vec16<T>::N]) { store16<T>(p, v); }
+};
+
+// <= 128 registers per thread => 4 CTAs (16 warps) per SM, each thread keeping CONV_U raw row loads in flight:
+// 16 warps * 8 loads * 512 B = 64 KB in flight per SM, above the ~45 KB that 6.5 TB/s needs at ~1 us latency.
 template <typename T, int K, bool SILU>
-__global__ void __launch_bounds__(CONV_THREADS)
+__global__ void __launch_bounds__(CONV_THREADS, 4)
 conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T* __restrict__ bias,
                   const T* __restrict__ init, T* __restrict__ out, T* __restrict__ fin,
                   int dim, int L, int64_t xbs, int64_t xss, int64_t obs, int64_t oss) {
@@ -32,26 +42,13 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
   x += (int64_t)b * xbs + c0;
   out += (int64_t)b * obs + c0;
 
-  // weights (dim, K) row-major: this thread's V*K values are contiguous -> K 16-byte loads
+  // weights (dim, K) row-major: this thread's V*K values are contiguous
   float w[K][V], bv[V];
-  {
-    float flat[K * V];
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      float tmp[V];
-      load16<T>(weight + (int64_t)c0 * K + i * V, tmp);
+  for (int v = 0; v < V; ++v) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) flat[i * V + j] = tmp[j];
-    }
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int k = 0; k < K; ++k) w[k][v] = flat[v * K + k];
-    if (bias != nullptr) load16<T>(bias + c0, bv);
-    else {
-#pragma unroll
-      for (int v = 0; v < V; ++v) bv[v] = 0.f;
-    }
+    for (int k = 0; k < K; ++k) w[k][v] = to_f32<T>(weight[(int64_t)(c0 + v) * K + k]);
+    bv[v] = bias != nullptr ? to_f32<T>(bias[c0 + v]) : 0.f;
   }
 
   // the K-1 rows preceding t0
@@ -60,7 +57,7 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
   for (int j = 0; j < K - 1; ++j) {
     const int t = t0 - (K - 1) + j;
     if (t >= 0) {
-      load16<T>(x + (int64_t)t * xss, win[j]);
+      Raw4<T> r; r.load(x + (int64_t)t * xss); r.unpack(win[j]);
     } else if (init != nullptr) {  // (b, dim, K-1): column t+(K-1) of the carried-in state
 #pragma unroll
       for (int v = 0; v < V; ++v)
@@ -72,29 +69,30 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
   }
 
   for (int tt = t0; tt < t1; tt += CONV_U) {
-    float xin[CONV_U][V];
+    Raw4<T> xin[CONV_U];
 #pragma unroll
     for (int u = 0; u < CONV_U; ++u)
-      if (tt + u < t1) load16<T>(x + (int64_t)(tt + u) * xss, xin[u]);
+      if (tt + u < t1) xin[u].load(x + (int64_t)(tt + u) * xss);
 #pragma unroll
     for (int u = 0; u < CONV_U; ++u) {
       if (tt + u < t1) {
-        float o[V];
+        float xv[V], o[V];
+        xin[u].unpack(xv);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           float acc = bv[v];
 #pragma unroll
           for (int k = 0; k < K - 1; ++k) acc = fmaf(w[k][v], win[k][v], acc);
-          acc = fmaf(w[K - 1][v], xin[u][v], acc);
+          acc = fmaf(w[K - 1][v], xv[v], acc);
           o[v] = SILU ? silu<FAST>(acc) : acc;
         }
-        store16<T>(out + (int64_t)(tt + u) * oss, o);
+        Raw4<T>::store(out + (int64_t)(tt + u) * oss, o);
 #pragma unroll
         for (int k = 0; k < K - 2; ++k)
 #pragma unroll
           for (int v = 0; v < V; ++v) win[k][v] = win[k + 1][v];
 #pragma unroll
-        for (int v = 0; v < V; ++v) win[K - 2][v] = xin[u][v];
+        for (int v = 0; v < V; ++v) win[K - 2][v] = xv[v];
       }
     }
   }
@@ -143,12 +141,15 @@ extern "C" int tv_causal_conv1d_fwd(const tv_conv1d_params* p, void* stream) {
   TV_CHECK_ARG(p->batch > 0 && p->dim > 0 && p->seqlen > 0, "causal_conv1d: empty problem (b=%d dim=%d L=%d)",
                p->batch, p->dim, p->seqlen);
   TV_CHECK_ARG(p->dtype == TV_F32 || p->dtype == TV_BF16, "causal_conv1d: dtype %d", p->dtype);
-  const int V = p->dtype == TV_BF16 ? 8 : 4;
+  const int V = 8;   // documented contract: 16-byte granularity for bf16 (the kernel itself needs 4 channels)
   const int esz = p->dtype == TV_BF16 ? 2 : 4;
-  TV_CHECK_ARG(p->dim % V == 0, "causal_conv1d: dim %d must be a multiple of %d", p->dim, V);
-  TV_CHECK_ARG(p->x_seq_stride % V == 0 && p->x_batch_stride % V == 0 && p->out_seq_stride % V == 0 &&
-                   p->out_batch_stride % V == 0,
-               "causal_conv1d: strides must be multiples of %d elements (16 bytes)", V);
+  TV_CHECK_ARG(p->dim % (p->dtype == TV_BF16 ? 8 : 4) == 0, "causal_conv1d: dim %d must be a multiple of %d", p->dim,
+               p->dtype == TV_BF16 ? 8 : 4);
+  const int SV = p->dtype == TV_BF16 ? 8 : 4;
+  TV_CHECK_ARG(p->x_seq_stride % SV == 0 && p->x_batch_stride % SV == 0 && p->out_seq_stride % SV == 0 &&
+                   p->out_batch_stride % SV == 0,
+               "causal_conv1d: strides must be multiples of %d elements (16 bytes)", SV);
+  (void)V;
   TV_CHECK_ARG(((uintptr_t)p->x % 16 == 0) && ((uintptr_t)p->out % 16 == 0) && ((uintptr_t)p->weight % 16 == 0) &&
                    (p->bias == nullptr || (uintptr_t)p->bias % 16 == 0),
                "causal_conv1d: x/out/weight/bias must be 16-byte aligned");

@@ -15,8 +15,29 @@ namespace tv {
 constexpr int NORM_WARPS = 8;
 constexpr int NORM_MAX_GROUP = 2048;  // elements of one group cached in a warp's registers (64 per lane)
 
+// Registers: the group's values must survive the reduction.  fp32 I/O keeps them in fp32 (64 per lane); bf16 I/O keeps
+// u = x*silu(z) re-packed as bf16x2 (32 per lane) -- the sum of squares is taken from the fp32 values BEFORE the
+// re-pack, so only the numerator sees one extra bf16 rounding -- which lifts residency from 2 to 3 CTAs per SM.
+template <typename T> struct Held;
+template <> struct Held<float> {
+  float v[4];
+  __device__ __forceinline__ void put(const float (&f)[4]) { for (int j = 0; j < 4; ++j) v[j] = f[j]; }
+  __device__ __forceinline__ void get(float (&f)[4]) const { for (int j = 0; j < 4; ++j) f[j] = v[j]; }
+};
+template <> struct Held<__nv_bfloat16> {
+  uint32_t v[4];
+  __device__ __forceinline__ void put(const float (&f)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+  }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = __uint_as_float(v[j] << 16); f[2 * j + 1] = __uint_as_float(v[j] & 0xffff0000u); }
+  }
+};
+
 template <typename T, bool HAS_Z, bool NORM_BEFORE_GATE, bool HAS_BIAS>
-__global__ void __launch_bounds__(NORM_WARPS * 32)
+__global__ void __launch_bounds__(NORM_WARPS * 32, sizeof(T) == 2 ? 3 : 2)
 gated_rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ z, const T* __restrict__ w,
                      const T* __restrict__ bias, T* __restrict__ out, int64_t rows, int ngroups,
                      int group_size, int64_t xrs, int64_t zrs, int64_t ors, float eps) {
@@ -34,21 +55,37 @@ gated_rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ z, const T* 
   const T* wp = w + (int64_t)g * group_size;
   T* op = out + row * ors + (int64_t)g * group_size;
 
-  float u[NORM_MAXV][V];   // x (norm_before_gate) or x*silu(z)
+  Held<T> held[NORM_MAXV];   // x (norm_before_gate) or x*silu(z)
   float ss = 0.f;
+  constexpr bool GATE_FIRST = HAS_Z && !NORM_BEFORE_GATE;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
-      load16<T>(xp + vi * V, u[i]);
-      if (HAS_Z && !NORM_BEFORE_GATE) {
-        float zz[V];
-        load16<T>(zp + vi * V, zz);
+  for (int half = 0; half < 2; ++half) {
+    // raw 16-byte loads of half the group are all issued before the first use (up to 8 independent loads per lane)
+    uint4 xr[NORM_MAXV / 2], zr[GATE_FIRST ? NORM_MAXV / 2 : 1];
 #pragma unroll
-        for (int j = 0; j < V; ++j) u[i][j] *= silu<FAST>(zz[j]);
+    for (int i = 0; i < NORM_MAXV / 2; ++i) {
+      const int vi = lane + 32 * (half * (NORM_MAXV / 2) + i);
+      if (vi < nvec) {
+        xr[i] = *reinterpret_cast<const uint4*>(xp + vi * V);
+        if (GATE_FIRST) zr[GATE_FIRST ? i : 0] = *reinterpret_cast<const uint4*>(zp + vi * V);
       }
+    }
 #pragma unroll
-      for (int j = 0; j < V; ++j) ss = fmaf(u[i][j], u[i][j], ss);
+    for (int i = 0; i < NORM_MAXV / 2; ++i) {
+      const int vi = lane + 32 * (half * (NORM_MAXV / 2) + i);
+      if (vi < nvec) {
+        float xv[V];
+        unpack16<T>(xr[i], xv);
+        if (GATE_FIRST) {
+          float zv[V];
+          unpack16<T>(zr[GATE_FIRST ? i : 0], zv);
+#pragma unroll
+          for (int j = 0; j < V; ++j) xv[j] *= silu<FAST>(zv[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) ss = fmaf(xv[j], xv[j], ss);
+        held[half * (NORM_MAXV / 2) + i].put(xv);
+      }
     }
   }
   ss = warp_sum(ss);
@@ -59,8 +96,9 @@ gated_rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ z, const T* 
     if (vi < nvec) {
       float ww[V], o[V];
       load16<T>(wp + vi * V, ww);
+      held[i].get(o);
 #pragma unroll
-      for (int j = 0; j < V; ++j) o[j] = u[i][j] * rstd * ww[j];
+      for (int j = 0; j < V; ++j) o[j] = o[j] * rstd * ww[j];
       if (HAS_BIAS) {
         float bb[V];
         load16<T>(bias + (int64_t)g * group_size + vi * V, bb);
