@@ -35,6 +35,9 @@ METRIC = "mamba2_mixer_prefill_tokens_per_s"
 UNIT = "tokens/s"
 # algorithmic bytes per token (SURVEY.md 8d / DESIGN.md), bf16, 9B dims
 BYTES_PER_TOKEN = {"conv1d": 49152, "ssd": 45312, "gated_rmsnorm": 61440}
+# per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from one `ncu --set full` capture of this
+# command at seqlen 131072 on 1 GPU (profiles/r01_summary.md); null for any other configuration
+NCU_TRAFFIC_128K = {"conv1d": 6.572e9, "ssd": 6.194e9, "gated_rmsnorm": 8.026e9}
 
 
 def peaks():
@@ -290,7 +293,9 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                         "frac": ach / pk["hbm_gbs"],
+                         "traffic": NCU_TRAFFIC_128K[dom] if (Ltot == 131072 and world == 1) else None,
+                         "traffic_source": "profiles/r01_summary.md (ncu --set full, per launch, bytes)", "peak_source": pk["source"],
                          "algorithmic_bytes_per_token": BYTES_PER_TOKEN[dom]},
             "kernels": kernels,
             "path_roofline": {"bytes_per_token": path_bytes,

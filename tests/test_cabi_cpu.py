@@ -112,3 +112,27 @@ def test_patch_reference_rebinds_all_gate_names():
     assert all((mod.selective_state_update, mod.mamba_chunk_scan_combined, mod.mamba_split_conv1d_scan_combined,
                 mod.causal_conv1d_fn, mod.causal_conv1d_update))                # the gate of modeling_nano.py:89-97
     assert mod.causal_conv1d_fn is tv.causal_conv1d_fn and mod.rmsnorm_fn is tv.rmsnorm_fn
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/timeviper"), reason="reference tree only exists in the build container")
+def test_patch_reference_on_the_real_module():
+    """The actual reference module (imported with the rmsnorm shim) takes its fast path after patching."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_shim"))
+    sys.path.insert(0, "/root/reference/timeviper/model/llm/llm_repo")
+    import nano.modeling_nano as mn
+    import timeviper_b200 as tv
+    assert not mn.is_fast_path_available
+    saved = {k: getattr(mn, k) for k in ("causal_conv1d_fn", "causal_conv1d_update", "mamba_chunk_scan_combined",
+                                         "mamba_split_conv1d_scan_combined", "selective_state_update", "rmsnorm_fn",
+                                         "is_fast_path_available")}
+    try:
+        tv.patch_reference(mn)
+        assert mn.is_fast_path_available and mn.mamba_chunk_scan_combined is tv.mamba_chunk_scan_combined
+        # the names the prefill branch calls (modeling_nano.py:619, :639, :372) resolve to this package
+        src = inspect.getsource(mn.NemotronHMamba2Mixer.cuda_kernels_forward)
+        for name in ("causal_conv1d_fn(", "mamba_chunk_scan_combined("):
+            assert name in src
+    finally:
+        for k, v in saved.items():
+            setattr(mn, k, v)

@@ -1,0 +1,83 @@
+"""Sequence-sharded mixer prefill over NCCL on >= 2 GPUs of one node (one process per GPU): every shard's output
+and the last rank's final states must equal the unsharded run on one GPU (there is no reference
+for multi-token continuation, so the oracle is W=1).  `pytest -m gpu`; skipped with fewer than 2 GPUs."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class _Cache:
+    conv_kernel_size = 4
+    conv = None
+    ssm = None
+    def update_conv_state(self, layer_idx, new_conv_state, cache_init=False): self.conv = new_conv_state
+    def update_ssm_state(self, layer_idx, new_ssm_state): self.ssm = new_ssm_state
+
+
+def _worker(rank, world, port, L, dtype_name, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import timeviper_b200 as tv
+        dtype = getattr(torch, dtype_name)
+        torch.manual_seed(99)
+        cfg = tv.Mamba2Config(hidden_size=256, mamba_num_heads=16, mamba_head_dim=80, n_groups=2,
+                              ssm_state_size=128, chunk_size=128)
+        mixer = tv.Mamba2MixerPrefill(cfg)
+        mixer.reset_parameters_like_reference()
+        with torch.no_grad():
+            mixer.A_log.copy_(torch.log(torch.rand(16) * 0.05 + 0.002))      # slow decay: boundary states matter
+            mixer.D.copy_(torch.randn(16))
+        mixer = mixer.to(dtype).cuda()
+        hs = torch.randn(1, L, 256).to(dtype).cuda()
+        with torch.no_grad():
+            full_cache = _Cache()
+            ref = mixer(hs, cache_params=full_cache)
+            sl = slice(rank * L // world, (rank + 1) * L // world)
+            cache = _Cache()
+            out = tv.sharded_mixer_forward(mixer, hs[:, sl].contiguous(), cache_params=cache)
+        torch.cuda.synchronize()
+        err = float((out.float() - ref[:, sl].float()).abs().max() / ref.float().abs().max())
+        res = {"rank": rank, "err": err}
+        if rank == world - 1:
+            res["ssm_err"] = float((cache.ssm - full_cache.ssm).abs().max() / full_cache.ssm.abs().max())
+            res["conv_equal"] = bool(torch.equal(cache.conv, full_cache.conv))
+        q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype_name,tol", [("bfloat16", 2e-2), ("float32", 1e-4)])
+def test_sharded_equals_unsharded_nccl(dtype_name, tol):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    L = 1024 * world
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, L, dtype_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in results:
+        assert r["err"] < tol, r
+        if r["rank"] == world - 1:
+            assert r["ssm_err"] < tol and r["conv_equal"], r
