@@ -36,8 +36,9 @@ constexpr uint32_t TILE_BC = Q * N * 2;          // 32768: two 16 KB halves (n 0
 constexpr uint32_t TILE_X = 5 * 4096;            // 20480: five 16-wide p atoms, SW32
 constexpr uint32_t XSTAGE = TILE_X + 1024;       // x tile | cs[128] f32 | dt[128] f32
 constexpr uint32_t OFF_B = 0, OFF_C = 2 * TILE_BC, OFF_X = 4 * TILE_BC;          // two buffers of each
-constexpr uint32_t OFF_XS = OFF_X + 2 * XSTAGE, OFF_S = OFF_XS + TILE_X, OFF_F = OFF_S + TILE_X;   // F: 2 x 512 B
-constexpr uint32_t OFF_D = OFF_F + 1024;          // 80 floats (D row), padded to 512
+constexpr uint32_t OFF_XS = OFF_X + 2 * XSTAGE, OFF_S = OFF_XS + TILE_X, OFF_F = OFF_S + TILE_X;
+constexpr uint32_t FBUF = 2048;                  // per buffer: F[128] | V1[128] | V2[128] | V3[128] (fp32)
+constexpr uint32_t OFF_D = OFF_F + 2 * FBUF;     // 80 floats (D row), padded to 512
 constexpr uint32_t OFF_BAR = OFF_D + 512;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + barriers + alignment slack
 static_assert(OFF_XS % 1024 == 0 && OFF_S % 1024 == 0 && XSTAGE % 256 == 0, "tile alignment");
@@ -104,6 +105,27 @@ __device__ __forceinline__ void m_block(uint32_t t_src, uint32_t t_dst, const fl
   uint32_t pk[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+  tmem_st16(t_dst, pk);
+}
+
+// Off-diagonal 32x32 block (every k of the block precedes every row of this warp): the decay factorises without
+// overflow around ref = cs at the last token before the warp's rows,
+//   exp(cs_m - cs_k) dt_k = u_m * v_k,   u_m = exp(cs_m - ref) <= 1,   v_k = dt_k exp(ref - cs_k) <= dt_k,
+// so the block costs two FMULs per element and NO transcendental (u_m: one exp per row, v_k: <= 3 per column per chunk).
+__device__ __forceinline__ void m_block_offdiag(uint32_t t_src, uint32_t t_dst, const float* __restrict__ sVk, float um) {
+  uint32_t r[32];
+  tmem_ld32(t_src, r);
+  float e[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 v4 = *reinterpret_cast<const float4*>(sVk + j);
+    e[j] = v4.x * um; e[j + 1] = v4.y * um; e[j + 2] = v4.z * um; e[j + 3] = v4.w * um;
+  }
+  tmem_ld_wait();
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    pk[j] = pack_bf16x2(e[2 * j] * __uint_as_float(r[2 * j]), e[2 * j + 1] * __uint_as_float(r[2 * j + 1]));
   tmem_st16(t_dst, pk);
 }
 
@@ -280,12 +302,18 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         const int s = c & 1, u = c >> 1;
         const float* sCS = reinterpret_cast<const float*>(smem + OFF_X + s * XSTAGE + TILE_X);
         const float* sDT = sCS + 128;
-        float* sF = reinterpret_cast<float*>(smem + OFF_F + s * 512);
+        float* sF = reinterpret_cast<float*>(smem + OFF_F + s * FBUF);
         mbar_wait(&bars[FULLX0 + s], u & 1);
-        const float Em = sCS[m] * LOG2E;
-        sF[m] = __log2f(sDT[m]) - Em;            // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
+        const float cs_m = sCS[m], dt_m = sDT[m];
+        const float Em = cs_m * LOG2E;
+        sF[m] = __log2f(dt_m) - Em;              // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
+        // v_k for the row quarters q that lie after this token's own quarter:  V_q[k] = dt_k exp(cs[32q-1] - cs_k)
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (q > warp) sF[q * 128 + m] = dt_m * ex2_approx((sCS[32 * q - 1] - cs_m) * LOG2E);
+        const float um = warp > 0 ? ex2_approx((cs_m - sCS[32 * warp - 1]) * LOG2E) : 0.f;   // u_m = exp(cs_m - ref)
         named_bar_sync(1, 128);
-        if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);   // cs/dt consumed by this warp (F lives in its own buffer)
+        if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);   // cs/dt consumed by this warp (F, V live in their own buffer)
         mbar_wait(&bars[CBFULL0 + s], u & 1);
         tc_fence_after();
         if (threadIdx.x == 0) TV_TRACE(5, c);
@@ -298,8 +326,10 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = 0u;
             tmem_st16(tcb + kb * 16, pk);
+          } else if (kb < warp) {
+            m_block_offdiag(tcb + kb * 32, tcb + kb * 16, sF + warp * 128 + kb * 32, um);
           } else {
-            m_block<DFOLD>(tcb + kb * 32, tcb + kb * 16, sF + kb * 32, Em, lane, Dh, kb == warp);
+            m_block<DFOLD>(tcb + kb * 32, tcb + kb * 16, sF + kb * 32, Em, lane, Dh, true);
           }
         }
         tmem_st_wait();
