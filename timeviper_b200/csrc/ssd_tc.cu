@@ -20,7 +20,7 @@
 // Warp roles (448 threads): warps 0-3 = WG_A (builds M), warps 4-7 = WG_B (x scaling, state decay, bf16 state
 // copy), warps 8-11 = WG_C (epilogue), warp 12 = TMA producer (+ L2 prefetch 3 chunks ahead), warp 13 = MMA
 // issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers so each is released as soon as
-// its last MMA has been issued.  Tensor-pipe order per iteration is S(c), D(c), G(c+1), O(c).
+// its last MMA has been issued.  Tensor-pipe order per iteration is S(c), O(c), D(c), G(c+1).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "ssd.h"
@@ -73,12 +73,12 @@ __device__ __forceinline__ uint32_t off_sw32(int r, int q) {  // row r, 16-byte 
 }
 }  // namespace tc
 
-// Tensor-pipe order per iteration c:  S(c)  D(c)  G(c+1)  O(c).
+// Tensor-pipe order per iteration c:  S(c)  O(c)  D(c)  G(c+1).
 //   S first: it is the loop-carried dependency (state);  its B tile is released right after it.
-//   D second: M(c) was built during the previous iteration; issuing it early releases the x stage early (x is
-//             the tile with the longest hold time: WG_B needs x(c+2) well before S(c+2)).
-//   G(c+1) third: look-ahead C.B^T; WG_A builds M(c+1) while O(c) and S(c+1) run.
-//   O last: needs the bf16 copy of S_c; releases the C tile and completes y of chunk c.
+//   O second: reads the bf16 copy of S_c, so that copy (single smem buffer) is free again by the time WG_B has the
+//             next entering state; releases the C tile.
+//   D third: M(c) was built during the previous iteration; completes y of chunk c and releases the x stage.
+//   G(c+1) last: look-ahead C.B^T; WG_A builds M(c+1) while S(c+1) and O(c+1) run.
 // One 32x32 block of M for this warp's 32 rows: M[m,k] = CB[m,k] * 2^(Em + F_k), masked to k <= m on the diagonal
 // block.  Written stage by stage (TMEM load, 32 exponent arguments, 32 MUFU.EX2, 32 FMUL, 16 packs, TMEM store) so
 // that the exp2 stream is issue-bound on the XU pipe (8 cycles per warp instruction) instead of latency-bound.
@@ -241,7 +241,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         tc_fence_after();
         TV_TRACE(1, c);
         const uint64_t so = (uint64_t)(s * (TILE_BC >> 4));
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           const uint64_t o = so + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
           umma_ss(tmem + (s ? T_CB1 : T_CB0), dC_k + o, dB_k + o, ID_CB, j > 0);
@@ -249,45 +249,48 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         umma_commit(&bars[CBFULL0 + s]);
       };
       if (FULL) issue_cb(0);
+#pragma unroll 1
       for (int c = 0; c < n; ++c) {
         const int s = c & 1, u = c >> 1;
+        const uint64_t so = (uint64_t)(s * (TILE_BC >> 4));
         // ---- S(c): state += B^T . xs
         mbar_wait(&bars[FULLB0 + s], u & 1);
         mbar_wait(&bars[SDECAY], c & 1);
         mbar_wait(&bars[XSFULL], c & 1);
         tc_fence_after();
         TV_TRACE(2, c);
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 8; ++j)
-          umma_ss(tmem + T_ST, dB_mn + (uint64_t)(s * (TILE_BC >> 4) + j * 128), dXS + (uint64_t)(j * 32), ID_ST, 1u);
+          umma_ss(tmem + T_ST, dB_mn + so + (uint64_t)(j * 128), dXS + (uint64_t)(j * 32), ID_ST, 1u);
         umma_commit(&bars[STDONE]);
         umma_commit(&bars[EMPTYB0 + s]);
         if (FULL) {
-          // ---- D(c): Yd = M . x   (A = M, packed bf16 in the first 64 columns of this chunk's CB buffer)
-          mbar_wait(&bars[FULLX0 + s], u & 1);
-          mbar_wait(&bars[MFULL0 + s], u & 1);
+          // ---- O(c): Yo = C . S_c
+          mbar_wait(&bars[FULLC0 + s], u & 1);
+          mbar_wait(&bars[SFULL], c & 1);
           if (c > 0) mbar_wait(&bars[YEMPTY], (c - 1) & 1);
           tc_fence_after();
-          TV_TRACE(4, c);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_ts(tmem + T_YD, tmem + (s ? T_CB1 : T_CB0) + j * 8,
-                    dX + (uint64_t)(s * (XSTAGE >> 4) + j * 32), ID_Y, j > 0);
-          umma_commit(&bars[EMPTYX0 + s]);
-          // ---- G(c+1)
-          if (c + 1 < n) issue_cb(c + 1);
-          // ---- O(c): Yo = C . S_c
-          mbar_wait(&bars[SFULL], c & 1);
-          tc_fence_after();
           TV_TRACE(3, c);
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < 8; ++j) {
-            const uint64_t o = (uint64_t)(s * (TILE_BC >> 4)) + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
+            const uint64_t o = so + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
             umma_ss(tmem + T_YO, dC_k + o, dS + (uint64_t)(j * 32), ID_Y, j > 0);
           }
           umma_commit(&bars[YOFFDONE]);
-          umma_commit(&bars[YFULL]);
           umma_commit(&bars[EMPTYC0 + s]);
+          // ---- D(c): Yd = M . x   (A = M, packed bf16 in the first 64 columns of this chunk's CB buffer)
+          mbar_wait(&bars[FULLX0 + s], u & 1);
+          mbar_wait(&bars[MFULL0 + s], u & 1);
+          tc_fence_after();
+          TV_TRACE(4, c);
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j)
+            umma_ts(tmem + T_YD, tmem + (s ? T_CB1 : T_CB0) + j * 8,
+                    dX + (uint64_t)(s * (XSTAGE >> 4) + j * 32), ID_Y, j > 0);
+          umma_commit(&bars[YFULL]);
+          umma_commit(&bars[EMPTYX0 + s]);
+          // ---- G(c+1)
+          if (c + 1 < n) issue_cb(c + 1);
         }
       }
     }
@@ -357,6 +360,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       const float a_c = __expf(cs_last);
       logsum += cs_last;
       const __nv_bfloat162 w2 = __float2bfloat162_rn(w_r);
+      // ---- xs = w_r * x into registers now (off the recurrence chain); stored once the xs buffer is free
       uint32_t xs[40];
 #pragma unroll
       for (int q = 0; q < 10; ++q) {
@@ -374,51 +378,37 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
 #pragma unroll
       for (int q = 0; q < 10; ++q)
         *reinterpret_cast<uint4*>(smem + OFF_XS + off_sw32(r, q)) = make_uint4(xs[4 * q], xs[4 * q + 1], xs[4 * q + 2], xs[4 * q + 3]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[XSFULL]);
-      // ---- state row n = r: decay in place (critical path), keep a bf16 copy of the un-decayed entering state
-      uint32_t spk[40];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {       // 48 + 32 columns: bounds registers, two TMEM round trips
-        const int c0 = half * 48, nc = half ? 2 : 3;
-        uint32_t v[48];
+      // ---- state row n = r: decay in place (critical path) and bf16 copy of the un-decayed entering state.
+      //      O(c-1) is issued right behind S(c-1), so the copy buffer is (almost always) already free here.
+      if (FULL && c > 0) mbar_wait(&bars[YOFFDONE], (c - 1) & 1);
+#pragma unroll 1
+      for (int pc = 0; pc < 5; ++pc) {            // rolled: keeps the loop body small in the I-cache
+        uint32_t v[16];
         if (c == 0) {
 #pragma unroll
-          for (int j = 0; j < 48; ++j)
-            if (j < nc * 16)
-              v[j] = a.init == nullptr ? 0u : __float_as_uint(a.init[(((int64_t)b * a.H + h) * P + c0 + j) * N + r]);
+          for (int j = 0; j < 16; ++j)
+            v[j] = a.init == nullptr ? 0u : __float_as_uint(a.init[(((int64_t)b * a.H + h) * P + pc * 16 + j) * N + r]);
         } else {
-#pragma unroll
-          for (int pc = 0; pc < 3; ++pc)
-            if (pc < nc) tmem_ld16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
+          tmem_ld16(tmem + T_ST + lane_base + pc * 16, v);
           tmem_ld_wait();
         }
+        if (FULL) {
+          uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 48; j += 2)
-          if (j < nc * 16) spk[(c0 + j) >> 1] = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, 2 * pc)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, 2 * pc + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
 #pragma unroll
-        for (int j = 0; j < 48; ++j)
-          if (j < nc * 16) v[j] = __float_as_uint(__uint_as_float(v[j]) * a_c);
-#pragma unroll
-        for (int pc = 0; pc < 3; ++pc)
-          if (pc < nc) tmem_st16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * a_c);
+        tmem_st16(tmem + T_ST + lane_base + pc * 16, v);
       }
       tmem_st_wait();
       tc_fence_before();
+      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[SDECAY]);
+      if (lane == 0) { mbar_arrive(&bars[XSFULL]); mbar_arrive(&bars[SDECAY]); if (FULL) mbar_arrive(&bars[SFULL]); }
       if (r == 0) TV_TRACE(9, c);
-      if (FULL) {
-        if (c > 0) mbar_wait(&bars[YOFFDONE], (c - 1) & 1);    // O(c-1) finished reading the bf16 state copy
-#pragma unroll
-        for (int q = 0; q < 10; ++q)
-          *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, q)) = make_uint4(spk[4 * q], spk[4 * q + 1], spk[4 * q + 2], spk[4 * q + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[SFULL]);
-        if (r == 0) TV_TRACE(10, c);
-      }
     }
     // ---- final state = state after the last chunk
     mbar_wait(&bars[STDONE], (n - 1) & 1);
@@ -445,74 +435,64 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         const int s = c & 1, u = c >> 1;
         const uint8_t* xst = smem + OFF_X + s * XSTAGE;
         const int t = c * Q + r;
-        float yv[80];                                // D * x (explicit path) or 0; then accumulates Yd + exp(cs_m) * Yo
         float e_r;
         if (!DFOLD) {
           mbar_wait(&bars[FULLX0 + s], u & 1);
           e_r = __expf(reinterpret_cast<const float*>(xst + TILE_X)[r]);
-#pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, q));
-            const float4 da = *reinterpret_cast<const float4*>(sD + 8 * q), db = *reinterpret_cast<const float4*>(sD + 8 * q + 4);
-            yv[8 * q + 0] = da.x * __uint_as_float(v.x << 16); yv[8 * q + 1] = da.y * __uint_as_float(v.x & 0xffff0000u);
-            yv[8 * q + 2] = da.z * __uint_as_float(v.y << 16); yv[8 * q + 3] = da.w * __uint_as_float(v.y & 0xffff0000u);
-            yv[8 * q + 4] = db.x * __uint_as_float(v.z << 16); yv[8 * q + 5] = db.y * __uint_as_float(v.z & 0xffff0000u);
-            yv[8 * q + 6] = db.z * __uint_as_float(v.w << 16); yv[8 * q + 7] = db.w * __uint_as_float(v.w & 0xffff0000u);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);
         } else {
           e_r = __expf(a.cs[(row0 + (int64_t)c * a.H) * Q + r]);   // one coalesced 512-byte row per chunk (L2 hit)
         }
-        uint32_t zk[HAS_Z ? 40 : 1];
-        if (HAS_Z) {
-          if (t < a.L) {
-            const uint4* zp = reinterpret_cast<const uint4*>(a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs);
-#pragma unroll
-            for (int q = 0; q < 10; ++q) {
-              const uint4 v = zp[q];
-              zk[(4 * q) % (HAS_Z ? 40 : 1)] = v.x; zk[(4 * q + 1) % (HAS_Z ? 40 : 1)] = v.y;
-              zk[(4 * q + 2) % (HAS_Z ? 40 : 1)] = v.z; zk[(4 * q + 3) % (HAS_Z ? 40 : 1)] = v.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < (HAS_Z ? 40 : 1); ++i) zk[i] = 0u;
-          }
-        }
+        const __nv_bfloat16* zrow = HAS_Z ? a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs : nullptr;
+        __nv_bfloat16* orow = a.out + (((int64_t)b * a.L + t) * a.H + h) * P;
         mbar_wait(&bars[YFULL], c & 1);
         tc_fence_after();
         if (r == 0) TV_TRACE(11, c);
-#pragma unroll
-        for (int pc = 0; pc < 5; ++pc) {
+#pragma unroll 1
+        for (int pc = 0; pc < 5; ++pc) {             // rolled: 16 columns (32 output bytes) per round
           uint32_t yd[16], yo[16];
           tmem_ld16(tmem + T_YD + lane_base + pc * 16, yd);
           tmem_ld16(tmem + T_YO + lane_base + pc * 16, yo);
-          tmem_ld_wait();
+          float xv[16];
+          if (!DFOLD) {                              // explicit D*x path ((H,P)-shaped D): x row from the x stage
+            const uint4 xa = *reinterpret_cast<const uint4*>(xst + off_sw32(r, 2 * pc));
+            const uint4 xb = *reinterpret_cast<const uint4*>(xst + off_sw32(r, 2 * pc + 1));
+            const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            yv[pc * 16 + j] = DFOLD ? fmaf(e_r, __uint_as_float(yo[j]), __uint_as_float(yd[j]))
-                                    : yv[pc * 16 + j] + fmaf(e_r, __uint_as_float(yo[j]), __uint_as_float(yd[j]));
+            for (int j = 0; j < 8; ++j) {
+              xv[2 * j] = sD[pc * 16 + 2 * j] * __uint_as_float(xw[j] << 16);
+              xv[2 * j + 1] = sD[pc * 16 + 2 * j + 1] * __uint_as_float(xw[j] & 0xffff0000u);
+            }
+          }
+          float zv[16];
+          if (HAS_Z) {
+            uint4 za = make_uint4(0, 0, 0, 0), zb = za;
+            if (t < a.L) { za = *reinterpret_cast<const uint4*>(zrow + pc * 16); zb = *reinterpret_cast<const uint4*>(zrow + pc * 16 + 8); }
+            const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              zv[2 * j] = silu<true>(__uint_as_float(zw[j] << 16));
+              zv[2 * j + 1] = silu<true>(__uint_as_float(zw[j] & 0xffff0000u));
+            }
+          }
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y0 = fmaf(e_r, __uint_as_float(yo[2 * j]), __uint_as_float(yd[2 * j]));
+            float y1 = fmaf(e_r, __uint_as_float(yo[2 * j + 1]), __uint_as_float(yd[2 * j + 1]));
+            if (!DFOLD) { y0 += xv[2 * j]; y1 += xv[2 * j + 1]; }
+            if (HAS_Z) { y0 *= zv[2 * j]; y1 *= zv[2 * j + 1]; }
+            pk[j] = pack_bf16x2(y0, y1);
+          }
+          if (t < a.L) st_global_v8(orow + pc * 16, pk);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[YEMPTY]);   // Yd / Yo may be overwritten
+        if (lane == 0) {
+          mbar_arrive(&bars[YEMPTY]);                // Yd / Yo may be overwritten
+          if (!DFOLD) mbar_arrive(&bars[EMPTYX0 + s]);
+        }
         if (r == 0) TV_TRACE(12, c);
-        uint32_t ypk[40];
-#pragma unroll
-        for (int j = 0; j < 80; j += 2) {
-          float y0 = yv[j], y1 = yv[j + 1];
-          if (HAS_Z) {
-            const uint32_t zp2 = zk[(j >> 1) % (HAS_Z ? 40 : 1)];
-            y0 *= silu<true>(__uint_as_float(zp2 << 16));
-            y1 *= silu<true>(__uint_as_float(zp2 & 0xffff0000u));
-          }
-          ypk[j >> 1] = pack_bf16x2(y0, y1);
-        }
-        if (t < a.L) {
-          __nv_bfloat16* op = a.out + (((int64_t)b * a.L + t) * a.H + h) * P;
-#pragma unroll
-          for (int q = 0; q < 5; ++q) st_global_v8(op + 16 * q, &ypk[8 * q]);
-        }
         if (r == 0) TV_TRACE(13, c);
       }
     }
