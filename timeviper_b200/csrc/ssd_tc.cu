@@ -17,9 +17,9 @@
 //      y[m,p]    = Yd + exp(cs_m) * Yo + D * x[m,p]   [* silu(z)]         WG_B epilogue -> global
 // Decay, mask and cumsum stay in fp32 registers; only the four contractions touch the tensor cores.
 //
-// Warp roles (448 threads): warps 0-3 = WG_A (builds M), warps 4-7 = WG_B (x scaling, state decay, bf16 state
-// copy), warps 8-11 = WG_C (epilogue), warp 12 = TMA producer (+ L2 prefetch 3 chunks ahead), warp 13 = MMA
-// issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers so each is released as soon as
+// Warp roles (576 threads): warps 0-3 = WG_A and 4-7 = WG_H (build M), warps 8-11 = WG_B (x scaling, state decay,
+// bf16 state copy), warps 12-15 = WG_C (epilogue), warp 16 = TMA producer (+ L2 prefetch 3 chunks ahead), warp 17 =
+// MMA issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers so each is released as soon as
 // its last MMA has been issued.  Tensor-pipe order per iteration is S(c), O(c), D(c), G(c+1).
 #include "common.cuh"
 #include "sm100.cuh"
@@ -31,23 +31,24 @@ using namespace sm100;
 
 namespace tc {
 constexpr int Q = 128, P = 80, N = 128;
-constexpr int THREADS = 448;                      // WG_A, WG_B, WG_C (4 warps each) + producer + MMA issuer
+constexpr int THREADS = 576;                      // WG_A, WG_H, WG_B, WG_C (4 warps each) + producer + MMA issuer
+constexpr int W_A = 0, W_H = 4, W_B = 8, W_C = 12, W_PROD = 16, W_MMA = 17;   // first warp of each role
 constexpr uint32_t TILE_BC = Q * N * 2;          // 32768: two 16 KB halves (n 0..63 | 64..127), SW128
 constexpr uint32_t TILE_X = 5 * 4096;            // 20480: five 16-wide p atoms, SW32
 constexpr uint32_t XSTAGE = TILE_X + 1024;       // x tile | cs[128] f32 | dt[128] f32
 constexpr uint32_t OFF_B = 0, OFF_C = 2 * TILE_BC, OFF_X = 4 * TILE_BC;          // two buffers of each
 constexpr uint32_t OFF_XS = OFF_X + 2 * XSTAGE, OFF_S = OFF_XS + TILE_X, OFF_F = OFF_S + TILE_X;
-constexpr uint32_t FBUF = 2048;                  // per buffer: F[128] | V1[128] | V2[128] | V3[128] (fp32)
+constexpr uint32_t FBUF = 2560;                  // per buffer: F[128] | V1[128] | V2[128] | V3[128] | U[128] (fp32)
 constexpr uint32_t OFF_D = OFF_F + 2 * FBUF;     // 80 floats (D row), padded to 512
 constexpr uint32_t OFF_BAR = OFF_D + 512;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + barriers + alignment slack
 static_assert(OFF_XS % 1024 == 0 && OFF_S % 1024 == 0 && XSTAGE % 256 == 0, "tile alignment");
 static_assert(SMEM_BYTES <= kMaxDynSmem, "smem budget");
 // TMEM columns
-constexpr uint32_t T_CB0 = 0, T_CB1 = 128, T_YD = 256, T_YO = 336, T_ST = 416;
+constexpr uint32_t T_CB = 0, T_M0 = 128, T_M1 = 192, T_YD = 256, T_YO = 336, T_ST = 416;   // M: 64 cols of packed bf16
 
 enum Bar { FULLB0 = 0, FULLB1, EMPTYB0, EMPTYB1, FULLC0, FULLC1, EMPTYC0, EMPTYC1, FULLX0, FULLX1, EMPTYX0, EMPTYX1,
-           CBFULL0, CBFULL1, MFULL0, MFULL1, XSFULL, SDECAY, SFULL, STDONE, YOFFDONE, YFULL, YEMPTY, NBAR };
+           CBFULL, CBEMPTY, MFULL0, MFULL1, FRDY0, FRDY1, XSFULL, SDECAY, SFULL, STDONE, YOFFDONE, YFULL, YEMPTY, NBAR };
 
 struct Maps { CUtensorMap x, b, c; };
 
@@ -151,14 +152,15 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       mbar_init(&bars[FULLB0 + i], 1); mbar_init(&bars[FULLC0 + i], 1); mbar_init(&bars[FULLX0 + i], 1);
       mbar_init(&bars[EMPTYB0 + i], 1); mbar_init(&bars[EMPTYC0 + i], 1);
       mbar_init(&bars[EMPTYX0 + i], FULL ? (DFOLD ? 9 : 13) : 4);   // one lane per consumer warp + the D(c) commit
-      mbar_init(&bars[CBFULL0 + i], 1); mbar_init(&bars[MFULL0 + i], 4);
+      mbar_init(&bars[MFULL0 + i], 8); mbar_init(&bars[FRDY0 + i], 4);
     }
+    mbar_init(&bars[CBFULL], 1); mbar_init(&bars[CBEMPTY], 8);
     mbar_init(&bars[XSFULL], 4); mbar_init(&bars[SDECAY], 4); mbar_init(&bars[SFULL], 4);
     mbar_init(&bars[STDONE], 1); mbar_init(&bars[YOFFDONE], 1); mbar_init(&bars[YFULL], 1);
     mbar_init(&bars[YEMPTY], 4);
     fence_mbar_init();
   }
-  if (warp == 13) tmem_alloc<512>(tmem_slot);
+  if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
   if (threadIdx.x < P) {
     float* sD = reinterpret_cast<float*>(smem + OFF_D);
     sD[threadIdx.x] = a.D == nullptr ? 0.f : (a.d_has_hdim ? a.D[h * P + threadIdx.x] : a.D[h]);
@@ -169,7 +171,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   const uint32_t tmem = *tmem_slot;
   const int64_t row0 = ((int64_t)b * n) * a.H + h;     // (b, c, h) row of dt_act / cs is row0 + c*H
 
-  if (warp == 12) {
+  if (warp == W_PROD) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       prefetch_tmap(&maps.x); prefetch_tmap(&maps.b);
@@ -220,7 +222,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         bulk_load(xs_ + TILE_X + 512, a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULLX0 + s]);
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == W_MMA) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
       constexpr uint32_t ID_CB = umma_idesc_bf16(128, 128, false, false);
@@ -238,15 +240,16 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         const int s = c & 1, u = c >> 1;
         mbar_wait(&bars[FULLB0 + s], u & 1);
         mbar_wait(&bars[FULLC0 + s], u & 1);
+        if (c > 0) mbar_wait(&bars[CBEMPTY], (c - 1) & 1);     // WG_A / WG_H have read CB(c-1) out of the single buffer
         tc_fence_after();
         TV_TRACE(1, c);
         const uint64_t so = (uint64_t)(s * (TILE_BC >> 4));
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           const uint64_t o = so + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
-          umma_ss(tmem + (s ? T_CB1 : T_CB0), dC_k + o, dB_k + o, ID_CB, j > 0);
+          umma_ss(tmem + T_CB, dC_k + o, dB_k + o, ID_CB, j > 0);
         }
-        umma_commit(&bars[CBFULL0 + s]);
+        umma_commit(&bars[CBFULL]);
       };
       if (FULL) issue_cb(0);
 #pragma unroll 1
@@ -278,14 +281,14 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           }
           umma_commit(&bars[YOFFDONE]);
           umma_commit(&bars[EMPTYC0 + s]);
-          // ---- D(c): Yd = M . x   (A = M, packed bf16 in the first 64 columns of this chunk's CB buffer)
+          // ---- D(c): Yd = M . x   (A = M(c), packed bf16, in its own TMEM buffer)
           mbar_wait(&bars[FULLX0 + s], u & 1);
           mbar_wait(&bars[MFULL0 + s], u & 1);
           tc_fence_after();
           TV_TRACE(4, c);
 #pragma unroll 1
           for (int j = 0; j < 8; ++j)
-            umma_ts(tmem + T_YD, tmem + (s ? T_CB1 : T_CB0) + j * 8,
+            umma_ts(tmem + T_YD, tmem + (s ? T_M1 : T_M0) + j * 8,
                     dX + (uint64_t)(s * (XSTAGE >> 4) + j * 32), ID_Y, j > 0);
           umma_commit(&bars[YFULL]);
           umma_commit(&bars[EMPTYX0 + s]);
@@ -294,58 +297,72 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         }
       }
     }
-  } else if (warp < 4) {
-    // =========================== WG_A: M = CB (.) decay, in place in TMEM ===========================
+  } else if (warp < W_B) {
+    // =========================== WG_A + WG_H: M = CB (.) decay, TMEM -> registers -> TMEM ===========================
+    // Row quarter q (TMEM lanes 32q..32q+31, i.e. SMSP q) owns q+1 blocks of 32 columns.  WG_A's warp q takes the
+    // diagonal block (the only one that needs exponentials) and block 2 of quarter 3; WG_H's warp q takes blocks
+    // 0 and 1 of quarters 2 and 3 and block 0 of quarter 1.  M(c) has its own TMEM buffer, so nothing is overwritten in
+    // place and the blocks above the diagonal are zeroed once, before the first chunk.
     if (FULL) {
-      const int m = threadIdx.x, lane = threadIdx.x & 31;
-      const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+      const bool helper = warp >= W_H;
+      const int q = warp & 3, lane = threadIdx.x & 31;
+      const int m = q * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
       constexpr float LOG2E = 1.4426950408889634f;
       const float Dh = (DFOLD && a.D != nullptr) ? a.D[h] : 0.f;
+      if (!helper) {                               // zero both M buffers once (columns above the diagonal stay zero)
+        uint32_t zz[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) zz[j] = 0u;
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) tmem_st16(tmem + T_M0 + lane_base + cb * 16, zz);
+        tmem_st_wait();
+      }
+      const int kb_lo = helper ? 0 : (q == 3 ? 2 : q);          // first block of this warp
+      const int kb_hi = helper ? (q == 3 ? 2 : (q == 0 ? 0 : q)) : q + 1;   // one past its last block
       for (int c = 0; c < n; ++c) {
         const int s = c & 1, u = c >> 1;
-        const float* sCS = reinterpret_cast<const float*>(smem + OFF_X + s * XSTAGE + TILE_X);
-        const float* sDT = sCS + 128;
         float* sF = reinterpret_cast<float*>(smem + OFF_F + s * FBUF);
-        mbar_wait(&bars[FULLX0 + s], u & 1);
-        const float cs_m = sCS[m], dt_m = sDT[m];
-        const float Em = cs_m * LOG2E;
-        sF[m] = __log2f(dt_m) - Em;              // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
-        // v_k for the row quarters q that lie after this token's own quarter:  V_q[k] = dt_k exp(cs[32q-1] - cs_k)
+        float Em = 0.f, um;
+        if (!helper) {
+          const float* sCS = reinterpret_cast<const float*>(smem + OFF_X + s * XSTAGE + TILE_X);
+          const float* sDT = sCS + 128;
+          mbar_wait(&bars[FULLX0 + s], u & 1);
+          const float cs_m = sCS[m], dt_m = sDT[m];
+          Em = cs_m * LOG2E;
+          sF[m] = __log2f(dt_m) - Em;            // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
+          // v_k for the row quarters that lie after this token's own quarter:  V_q'[k] = dt_k exp(cs[32q'-1] - cs_k)
 #pragma unroll
-        for (int q = 1; q < 4; ++q)
-          if (q > warp) sF[q * 128 + m] = dt_m * ex2_approx((sCS[32 * q - 1] - cs_m) * LOG2E);
-        const float um = warp > 0 ? ex2_approx((cs_m - sCS[32 * warp - 1]) * LOG2E) : 0.f;   // u_m = exp(cs_m - ref)
-        named_bar_sync(1, 128);
-        if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);   // cs/dt consumed by this warp (F, V live in their own buffer)
-        mbar_wait(&bars[CBFULL0 + s], u & 1);
+          for (int qq = 1; qq < 4; ++qq)
+            if (qq > q) sF[qq * 128 + m] = dt_m * ex2_approx((sCS[32 * qq - 1] - cs_m) * LOG2E);
+          um = q > 0 ? ex2_approx((cs_m - sCS[32 * q - 1]) * LOG2E) : 0.f;     // u_m = exp(cs_m - ref) <= 1
+          sF[4 * 128 + m] = um;
+          named_bar_sync(1, 128);
+          if (lane == 0) { mbar_arrive(&bars[FRDY0 + s]); mbar_arrive(&bars[EMPTYX0 + s]); }
+        } else {
+          mbar_wait(&bars[FRDY0 + s], u & 1);
+          um = sF[4 * 128 + m];
+        }
+        mbar_wait(&bars[CBFULL], c & 1);
         tc_fence_after();
         if (threadIdx.x == 0) TV_TRACE(5, c);
-        if (threadIdx.x == 96) TV_TRACE(16 * n + 0, c);
-        const uint32_t tcb = tmem + (s ? T_CB1 : T_CB0) + lane_base;
+        const uint32_t tcb = tmem + T_CB + lane_base;
+        const uint32_t tm = tmem + (s ? T_M1 : T_M0) + lane_base;
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {         // rolled on purpose: one copy of the block body in the I-cache
-          if (kb > warp) {                       // whole 32x32 block above the diagonal: M = 0
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
-            tmem_st16(tcb + kb * 16, pk);
-          } else if (kb < warp) {
-            m_block_offdiag(tcb + kb * 32, tcb + kb * 16, sF + warp * 128 + kb * 32, um);
-          } else {
-            m_block<DFOLD>(tcb + kb * 32, tcb + kb * 16, sF + kb * 32, Em, lane, Dh, true);
-          }
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {   // rolled on purpose: one copy of each block body in the I-cache
+          if (kb < q) m_block_offdiag(tcb + kb * 32, tm + kb * 16, sF + q * 128 + kb * 32, um);
+          else m_block<DFOLD>(tcb + kb * 32, tm + kb * 16, sF + kb * 32, Em, lane, Dh, true);
         }
         tmem_st_wait();
-        if (threadIdx.x == 96) TV_TRACE(16 * n + 13, c);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[MFULL0 + s]);
+        if (lane == 0) { mbar_arrive(&bars[MFULL0 + s]); mbar_arrive(&bars[CBEMPTY]); }
         if (threadIdx.x == 0) TV_TRACE(6, c);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < W_C) {
     // =========================== WG_B: xs = w.x, state decay and bf16 state copy ===========================
-    const int r = threadIdx.x - 128, lane = threadIdx.x & 31;   // token row of x / state row n
+    const int r = threadIdx.x - W_B * 32, lane = threadIdx.x & 31;   // token row of x / state row n
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     float logsum = 0.f;
     for (int c = 0; c < n; ++c) {
@@ -425,10 +442,10 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       }
     }
     if (a.logdecay != nullptr && r == 0) a.logdecay[(int64_t)b * a.H + h] = logsum;
-  } else if (warp < 12) {
+  } else if (warp < W_PROD) {
     // =========================== WG_C: epilogue  y = Yd + exp(cs_m) Yo + D x  [* silu(z)] ===========================
     if (FULL) {
-      const int r = threadIdx.x - 256, lane = threadIdx.x & 31;   // token row m
+      const int r = threadIdx.x - W_C * 32, lane = threadIdx.x & 31;   // token row m
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       const float* sD = reinterpret_cast<const float*>(smem + OFF_D);
       for (int c = 0; c < n; ++c) {
@@ -499,7 +516,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) tmem_dealloc<512>(tmem);
+  if (warp == W_MMA) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------ host
