@@ -188,6 +188,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// descriptor whose 14-bit start-address field is advanced by `off16` units of 16 bytes (32-bit add on the low word:
+// shared-memory addresses stay below 2^18, so no carry reaches the other fields)
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t off16) {
+  uint32_t lo = (uint32_t)desc + off16, hi = (uint32_t)(desc >> 32);
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {

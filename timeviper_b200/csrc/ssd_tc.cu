@@ -236,6 +236,8 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       const uint64_t dX = umma_smem_desc(sbase + OFF_X, 4096, 256, SWZ_32B);
       const uint64_t dXS = umma_smem_desc(sbase + OFF_XS, 4096, 256, SWZ_32B);
       const uint64_t dS = umma_smem_desc(sbase + OFF_S, 4096, 256, SWZ_32B);
+      // The issue loops are fully unrolled with compile-time descriptor offsets: a rolled loop costs ~110 cycles per
+      // MMA on the single issuing thread (descriptor arithmetic + R2UR), which made issue the bottleneck.
       auto issue_cb = [&](int c) {   // G(c): CB = C . B^T
         const int s = c & 1, u = c >> 1;
         mbar_wait(&bars[FULLB0 + s], u & 1);
@@ -243,11 +245,12 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         if (c > 0) mbar_wait(&bars[CBEMPTY], (c - 1) & 1);     // WG_A / WG_H have read CB(c-1) out of the single buffer
         tc_fence_after();
         TV_TRACE(1, c);
-        const uint64_t so = (uint64_t)(s * (TILE_BC >> 4));
-#pragma unroll 1
+        const uint32_t so = (uint32_t)(s * (TILE_BC >> 4));
+        const uint64_t dc = umma_desc_advance(dC_k, so), db = umma_desc_advance(dB_k, so);
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint64_t o = so + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
-          umma_ss(tmem + T_CB, dC_k + o, dB_k + o, ID_CB, j > 0);
+          const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
+          umma_ss(tmem + T_CB, umma_desc_advance(dc, o), umma_desc_advance(db, o), ID_CB, j > 0);
         }
         umma_commit(&bars[CBFULL]);
       };
@@ -255,16 +258,19 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
 #pragma unroll 1
       for (int c = 0; c < n; ++c) {
         const int s = c & 1, u = c >> 1;
-        const uint64_t so = (uint64_t)(s * (TILE_BC >> 4));
+        const uint32_t so = (uint32_t)(s * (TILE_BC >> 4));
         // ---- S(c): state += B^T . xs
         mbar_wait(&bars[FULLB0 + s], u & 1);
         mbar_wait(&bars[SDECAY], c & 1);
         mbar_wait(&bars[XSFULL], c & 1);
         tc_fence_after();
         TV_TRACE(2, c);
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j)
-          umma_ss(tmem + T_ST, dB_mn + so + (uint64_t)(j * 128), dXS + (uint64_t)(j * 32), ID_ST, 1u);
+        {
+          const uint64_t db = umma_desc_advance(dB_mn, so);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_ss(tmem + T_ST, umma_desc_advance(db, j * 128), umma_desc_advance(dXS, j * 32), ID_ST, 1u);
+        }
         umma_commit(&bars[STDONE]);
         umma_commit(&bars[EMPTYB0 + s]);
         if (FULL) {
@@ -274,10 +280,13 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           if (c > 0) mbar_wait(&bars[YEMPTY], (c - 1) & 1);
           tc_fence_after();
           TV_TRACE(3, c);
-#pragma unroll 1
-          for (int j = 0; j < 8; ++j) {
-            const uint64_t o = so + (uint64_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
-            umma_ss(tmem + T_YO, dC_k + o, dS + (uint64_t)(j * 32), ID_Y, j > 0);
+          {
+            const uint64_t dc = umma_desc_advance(dC_k, so);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
+              umma_ss(tmem + T_YO, umma_desc_advance(dc, o), umma_desc_advance(dS, j * 32), ID_Y, j > 0);
+            }
           }
           umma_commit(&bars[YOFFDONE]);
           umma_commit(&bars[EMPTYC0 + s]);
@@ -286,10 +295,12 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           mbar_wait(&bars[MFULL0 + s], u & 1);
           tc_fence_after();
           TV_TRACE(4, c);
-#pragma unroll 1
-          for (int j = 0; j < 8; ++j)
-            umma_ts(tmem + T_YD, tmem + (s ? T_M1 : T_M0) + j * 8,
-                    dX + (uint64_t)(s * (XSTAGE >> 4) + j * 32), ID_Y, j > 0);
+          {
+            const uint64_t dx = umma_desc_advance(dX, (uint32_t)(s * (XSTAGE >> 4)));
+            const uint32_t tmA = tmem + (s ? T_M1 : T_M0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) umma_ts(tmem + T_YD, tmA + j * 8, umma_desc_advance(dx, j * 32), ID_Y, j > 0);
+          }
           umma_commit(&bars[YFULL]);
           umma_commit(&bars[EMPTYX0 + s]);
           // ---- G(c+1)

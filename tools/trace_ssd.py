@@ -33,11 +33,3 @@ for e, nm in enumerate(names):
     rel = (t[c0:c1, e] - t[c0:c1, 2]).float().mean().item()
     print(f"  {nm:>16} relative to S issue of same chunk: {rel:10.0f}")
 
-print("WG_A warp 3 (thread 96): block starts kb=0..3 relative to its cbfull, then done")
-for c in range(c0, c0 + 3):
-    base = int(ta[c, 0])
-    print(c, [int(ta[c, e]) - base for e in (1, 2, 3, 4, 13)])
-print("WG_A warp 0 (thread 0): block starts kb=0..3 relative to its cbfull, blocks done, st_wait done")
-for c in range(c0, c0 + 3):
-    base = int(ta[c, 5])
-    print(c, [int(ta[c, e]) - base for e in (6, 7, 8, 9, 10, 11)])
