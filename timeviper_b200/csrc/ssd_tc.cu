@@ -409,27 +409,39 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       // ---- state row n = r: decay in place (critical path) and bf16 copy of the un-decayed entering state.
       //      O(c-1) is issued right behind S(c-1), so the copy buffer is (almost always) already free here.
       if (FULL && c > 0) mbar_wait(&bars[YOFFDONE], (c - 1) & 1);
-#pragma unroll 1
-      for (int pc = 0; pc < 5; ++pc) {            // rolled: keeps the loop body small in the I-cache
-        uint32_t v[16];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {       // 48 + 32 columns: two TMEM round trips instead of five
+        const int c0 = half * 48, nc = half ? 2 : 3;
+        uint32_t v[48];
         if (c == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = a.init == nullptr ? 0u : __float_as_uint(a.init[(((int64_t)b * a.H + h) * P + pc * 16 + j) * N + r]);
+          for (int j = 0; j < 48; ++j)
+            if (j < nc * 16)
+              v[j] = a.init == nullptr ? 0u : __float_as_uint(a.init[(((int64_t)b * a.H + h) * P + c0 + j) * N + r]);
         } else {
-          tmem_ld16(tmem + T_ST + lane_base + pc * 16, v);
+#pragma unroll
+          for (int pc = 0; pc < 3; ++pc)
+            if (pc < nc) tmem_ld16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
           tmem_ld_wait();
         }
         if (FULL) {
-          uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, 2 * pc)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, 2 * pc + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          for (int q = 0; q < 6; ++q)
+            if (q < 2 * nc) {
+              const int j = 8 * q;
+              *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, (c0 >> 3) + q)) =
+                  make_uint4(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                             pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
+                             pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
+                             pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * a_c);
-        tmem_st16(tmem + T_ST + lane_base + pc * 16, v);
+        for (int j = 0; j < 48; ++j)
+          if (j < nc * 16) v[j] = __float_as_uint(__uint_as_float(v[j]) * a_c);
+#pragma unroll
+        for (int pc = 0; pc < 3; ++pc)
+          if (pc < nc) tmem_st16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
       }
       tmem_st_wait();
       tc_fence_before();
@@ -475,11 +487,13 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         mbar_wait(&bars[YFULL], c & 1);
         tc_fence_after();
         if (r == 0) TV_TRACE(11, c);
-#pragma unroll 1
-        for (int pc = 0; pc < 5; ++pc) {             // rolled: 16 columns (32 output bytes) per round
-          uint32_t yd[16], yo[16];
-          tmem_ld16(tmem + T_YD + lane_base + pc * 16, yd);
-          tmem_ld16(tmem + T_YO + lane_base + pc * 16, yo);
+        // Software-pipelined drain: the TMEM loads of round pc+1 are in flight while round pc is combined and stored;
+        // the accumulators are handed back as soon as the last load has landed, before the last round's math.
+        uint32_t ydA[16], yoA[16], ydB[16], yoB[16];
+        tmem_ld16(tmem + T_YD + lane_base, ydA);
+        tmem_ld16(tmem + T_YO + lane_base, yoA);
+        tmem_ld_wait();
+        auto finish_round = [&](int pc, const uint32_t (&yd)[16], const uint32_t (&yo)[16]) {
           float xv[16];
           if (!DFOLD) {                              // explicit D*x path ((H,P)-shaped D): x row from the x stage
             const uint4 xa = *reinterpret_cast<const uint4*>(xst + off_sw32(r, 2 * pc));
@@ -502,7 +516,6 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
               zv[2 * j + 1] = silu<true>(__uint_as_float(zw[j] & 0xffff0000u));
             }
           }
-          tmem_ld_wait();
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -513,13 +526,30 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
             pk[j] = pack_bf16x2(y0, y1);
           }
           if (t < a.L) st_global_v8(orow + pc * 16, pk);
+        };
+#pragma unroll
+        for (int pc = 0; pc < 5; pc += 2) {
+          if (pc + 1 < 5) {
+            tmem_ld16(tmem + T_YD + lane_base + (pc + 1) * 16, ydB);
+            tmem_ld16(tmem + T_YO + lane_base + (pc + 1) * 16, yoB);
+          }
+          finish_round(pc, ydA, yoA);
+          if (pc + 1 < 5) {
+            tmem_ld_wait();
+            if (pc + 2 < 5) {
+              tmem_ld16(tmem + T_YD + lane_base + (pc + 2) * 16, ydA);
+              tmem_ld16(tmem + T_YO + lane_base + (pc + 2) * 16, yoA);
+            }
+            finish_round(pc + 1, ydB, yoB);
+            if (pc + 2 < 5) tmem_ld_wait();
+          }
+          if (pc + 2 == 4) {                           // the last loads (round 4) have landed: release Yd / Yo now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[YEMPTY]);
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bars[YEMPTY]);                // Yd / Yo may be overwritten
-          if (!DFOLD) mbar_arrive(&bars[EMPTYX0 + s]);
-        }
+        if (!DFOLD) { __syncwarp(); if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]); }
         if (r == 0) TV_TRACE(12, c);
         if (r == 0) TV_TRACE(13, c);
       }

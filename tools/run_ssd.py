@@ -7,7 +7,9 @@ from tests.test_gpu_ops import _ssd_inputs
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(1, L, 128, 80, 8, 128, torch.bfloat16, seed=1)
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+G = int(sys.argv[4]) if len(sys.argv) > 4 else 8
+x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(1, L, H, 80, G, 128, torch.bfloat16, seed=1)
 for _ in range(2):
     tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, dt_bias=dt_bias, dt_softplus=True, return_final_states=True)
 torch.cuda.synchronize()
@@ -17,4 +19,4 @@ for _ in range(iters):
     tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, dt_bias=dt_bias, dt_softplus=True, return_final_states=True)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
-print(f"L={L} ssd {ms:.3f} ms  {45312*L/ms/1e6:.1f} GB/s  {ms*1e3/ (L/128):.2f} us/chunk")
+print(f"L={L} H={H} G={G} ssd {ms:.3f} ms  {(45312/128*H)*L/ms/1e6:.1f} GB/s  {ms*1e3/ (L/128):.2f} us/chunk")
