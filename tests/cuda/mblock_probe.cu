@@ -6,7 +6,9 @@
 using namespace tv::sm100;
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&t); }
 
-__device__ __forceinline__ void m_block(uint32_t t_src, uint32_t t_dst, const float* __restrict__ sFk, float Em, int lane, float Dh, bool diag) {
+template <int ID>
+__device__ __noinline__ void m_block(uint32_t t_src, uint32_t t_dst, const float* __restrict__ sFk, float Em, int lane, float Dh, bool diag) {
+  asm volatile("// copy %0" :: "n"(ID));
   uint32_t r[32];
   tmem_ld32(t_src, r);
   float e[32];
@@ -58,7 +60,14 @@ __global__ void __launch_bounds__(384) k(long long* out, int mode, int nthreads_
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < 64; ++it) {
-      if (mode == 0) m_block(tcb + (it & 3) * 32, tcb + (it & 3) * 16, sF + (it & 3) * 32, -0.3f * lane, lane, 1.0f, true);
+      if (mode == 0) m_block<0>(tcb + (it & 3) * 32, tcb + (it & 3) * 16, sF + (it & 3) * 32, -0.3f * lane, lane, 1.0f, true);
+      else if (mode == 2) {   // every warp runs its own copy of the code (12 distinct copies: 3 per SMSP)
+        switch (warp) {
+#define CASE(W) case W: m_block<W + 1>(tcb + (it & 3) * 32, tcb + (it & 3) * 16, sF + (it & 3) * 32, -0.3f * lane, lane, 1.0f, true); break;
+          CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11)
+#undef CASE
+        }
+      }
       else m_block_offdiag(tcb + (it & 3) * 32, tcb + (it & 3) * 16, sF + (it & 3) * 32, 0.5f);
     }
     tmem_st_wait();
@@ -70,11 +79,12 @@ __global__ void __launch_bounds__(384) k(long long* out, int mode, int nthreads_
 }
 int main() {
   long long* d; cudaMalloc(&d, 128); cudaMemset(d, 0, 128);
-  for (int mode = 0; mode < 2; ++mode) { k<<<1, 384>>>(d, mode, 128); k<<<1, 384>>>(d, mode, 384); }
+  for (int mode = 0; mode < 3; ++mode) { k<<<1, 384>>>(d, mode, 128); k<<<1, 384>>>(d, mode, 384); }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
   long long h[16]; cudaMemcpy(h, d, 128, cudaMemcpyDeviceToHost);
   printf("diag block   : %lld cycles (1 warp/SMSP), %lld cycles (3 warps/SMSP)\n", h[0], h[1]);
+  printf("diag block, distinct code copy per warp (noinline): %lld cycles (1 warp/SMSP), %lld cycles (3 warps/SMSP)\n", h[8], h[9]);
   printf("offdiag block: %lld cycles (1 warp/SMSP), %lld cycles (3 warps/SMSP)\n", h[4], h[5]);
   return 0;
 }

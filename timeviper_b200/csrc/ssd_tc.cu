@@ -560,6 +560,176 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   if (warp == W_MMA) tmem_dealloc<512>(tmem);
 }
 
+
+// =================================================================================================================
+// Shard summary (pass 1 of the sequence-sharded prefill): final state from a zero initial state + sum of dt*A.
+//
+// No recurrence is needed for this: with T_c = sum of the chunk totals of all LATER chunks (<= 0),
+//   S_final[n,p] = sum_c sum_k B[k,n] * x[k,p] * dt_k * exp(cs_last(c) - cs_k + T_c)
+// is ONE long-K GEMM accumulated in TMEM (every weight is <= dt_k, so nothing overflows), the chunks can be taken
+// in any order, and a chunk whose T_c has underflowed fp32 contributes exactly zero.  The kernel therefore walks
+// the chunks BACKWARDS from the end of the shard and stops at first_chunk[b,h], the first chunk whose suffix decay is
+// still representable (ssd_suffix_scan_kernel).  For fast-decaying heads that is 1-3 chunks, whatever the shard length.
+// =================================================================================================================
+constexpr float kLogUnderflow = -104.f;   // exp(x) == 0 in fp32 (incl. denormals) for x < -103.98
+
+// one warp per (b, h): logdecay_sum = sum_c cs_last(c);  first_chunk = smallest c with T_c >= kLogUnderflow
+__global__ void __launch_bounds__(128)
+ssd_suffix_scan_kernel(const float* __restrict__ cs, float* __restrict__ logdecay, int* __restrict__ first_chunk,
+                       int BH, int H, int nchunks, int Q) {
+  const int bh = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (bh >= BH) return;
+  const int b = bh / H, h = bh - b * H;
+  const float* base = cs + (((int64_t)b * nchunks) * H + h) * Q + (Q - 1);     // chunk c at + c*H*Q
+  float carry = 0.f;            // sum of the totals of chunks after the current block of 32
+  int first = 0;
+  bool found = false;
+  for (int hi = nchunks; hi > 0; hi -= 32) {          // blocks of 32 chunks, from the end
+    const int c = hi - 1 - lane;                      // lane 0 = last chunk of the block
+    const float v = c >= 0 ? base[(int64_t)c * H * Q] : 0.f;
+    float incl = v;                                   // inclusive scan over lanes = suffix sum over chunks
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const float Tc = carry + incl - v;                // sum over chunks strictly after c
+    const unsigned dead = __ballot_sync(0xffffffffu, c >= 0 && Tc < kLogUnderflow);
+    if (!found && dead != 0u) {                       // lowest dead lane = latest dead chunk: everything before is dead too
+      first = hi - 1 - (__ffs(dead) - 1) + 1;
+      found = true;
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    if (logdecay != nullptr) logdecay[bh] = carry;
+    first_chunk[bh] = found ? first : 0;
+  }
+}
+
+namespace st {
+constexpr int THREADS = 192;                     // warps 0-3: x scaling, warp 4: TMA producer, warp 5: MMA issuer
+constexpr uint32_t OFF_B = 0, OFF_X = 2 * tc::TILE_BC, OFF_XS = OFF_X + 2 * tc::XSTAGE;
+constexpr uint32_t OFF_BAR = OFF_XS + 2 * tc::TILE_X;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;
+enum Bar { FULL0 = 0, FULL1, EMPTY0, EMPTY1, XSFULL0, XSFULL1, XSEMPTY0, XSEMPTY1, DONE, NBAR };
+static_assert(OFF_XS % 1024 == 0, "tile alignment");
+}  // namespace st
+
+__global__ void __launch_bounds__(st::THREADS, 1)
+ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const int* __restrict__ first_chunk) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + st::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + st::OFF_BAR + st::NBAR * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int g = h / (a.H / a.G);
+  const int n = a.nchunks;
+  const int c_first = first_chunk[(int64_t)b * a.H + h];
+  const int count = n - c_first;                       // chunks n-1, n-2, ..., c_first
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[st::FULL0 + i], 1); mbar_init(&bars[st::EMPTY0 + i], 5);      // 4 scaling warps + the MMA commit
+      mbar_init(&bars[st::XSFULL0 + i], 4); mbar_init(&bars[st::XSEMPTY0 + i], 1);
+    }
+    mbar_init(&bars[st::DONE], 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t row0 = ((int64_t)b * n) * a.H + h;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      prefetch_tmap(&maps.x); prefetch_tmap(&maps.b);
+      for (int i = 0; i < count; ++i) {
+        const int c = n - 1 - i, s = i & 1, u = i >> 1;
+        if (i >= 2) mbar_wait(&bars[st::EMPTY0 + s], (u - 1) & 1);
+        uint8_t* sb = smem + st::OFF_B + s * TILE_BC;
+        uint8_t* sx = smem + st::OFF_X + s * XSTAGE;
+        mbar_arrive_expect_tx(&bars[st::FULL0 + s], TILE_BC + XSTAGE);
+        const int t0 = c * Q;
+        tma_load_4d(sb, &maps.b, &bars[st::FULL0 + s], 0, g, t0, b);
+        tma_load_4d(sb + 16384, &maps.b, &bars[st::FULL0 + s], 64, g, t0, b);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) tma_load_4d(sx + j * 4096, &maps.x, &bars[st::FULL0 + s], 16 * j, h, t0, b);
+        bulk_load(sx + TILE_X, a.cs + (row0 + (int64_t)c * a.H) * Q, 512, &bars[st::FULL0 + s]);
+        bulk_load(sx + TILE_X + 512, a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512, &bars[st::FULL0 + s]);
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t ID_ST = umma_idesc_bf16(128, P, true, true);
+      const uint32_t sbase = smem_u32(smem);
+      const uint64_t dB = umma_smem_desc(sbase + st::OFF_B, 16384, 1024, SWZ_128B);
+      const uint64_t dXS = umma_smem_desc(sbase + st::OFF_XS, 4096, 256, SWZ_32B);
+#pragma unroll 1
+      for (int i = 0; i < count; ++i) {
+        const int s = i & 1, u = i >> 1;
+        mbar_wait(&bars[st::FULL0 + s], u & 1);
+        mbar_wait(&bars[st::XSFULL0 + s], u & 1);
+        tc_fence_after();
+        const uint64_t db = umma_desc_advance(dB, (uint32_t)(s * (TILE_BC >> 4)));
+        const uint64_t dx = umma_desc_advance(dXS, (uint32_t)(s * (TILE_X >> 4)));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tmem, umma_desc_advance(db, j * 128), umma_desc_advance(dx, j * 32), ID_ST, (i > 0 || j > 0) ? 1u : 0u);
+        umma_commit(&bars[st::EMPTY0 + s]);
+        umma_commit(&bars[st::XSEMPTY0 + s]);
+      }
+      umma_commit(&bars[st::DONE]);
+    }
+  } else {
+    // ---- x scaling: xs[k,p] = x[k,p] * dt_k * exp(cs_last - cs_k + T_c), T_c = totals of the chunks already visited
+    const int r = threadIdx.x;
+    float T = 0.f;
+    for (int i = 0; i < count; ++i) {
+      const int s = i & 1, u = i >> 1;
+      const uint8_t* xst = smem + st::OFF_X + s * XSTAGE;
+      const float* sCS = reinterpret_cast<const float*>(xst + TILE_X);
+      const float* sDT = sCS + 128;
+      mbar_wait(&bars[st::FULL0 + s], u & 1);
+      const float cs_last = sCS[Q - 1];
+      const float w_r = sDT[r] * __expf(cs_last - sCS[r] + T);
+      T += cs_last;
+      const __nv_bfloat162 w2 = __float2bfloat162_rn(w_r);
+      if (i >= 2) mbar_wait(&bars[st::XSEMPTY0 + s], (u - 1) & 1);
+      uint8_t* xs_out = smem + st::OFF_XS + s * TILE_X;
+#pragma unroll
+      for (int q = 0; q < 10; ++q) {
+        uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, q));
+        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hv[j] = __hmul2(hv[j], w2);
+        *reinterpret_cast<uint4*>(xs_out + off_sw32(r, q)) = v;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bars[st::XSFULL0 + s]); mbar_arrive(&bars[st::EMPTY0 + s]); }
+    }
+    mbar_wait(&bars[st::DONE], 0);
+    tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll
+    for (int pc = 0; pc < 5; ++pc) {
+      uint32_t v[16];
+      tmem_ld16(tmem + lane_base + pc * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        a.fin[(((int64_t)b * a.H + h) * P + pc * 16 + j) * N + r] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<128>(tmem);
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static void* g_trace_ptr = nullptr;   // debug: device buffer of nchunks*16 int64 (tv_debug_set_trace)
 void set_trace_buffer(void* p) { g_trace_ptr = p; }
@@ -580,7 +750,7 @@ bool tc_supported(const tv_ssd_params& p) {
 size_t tc_workspace_bytes(const tv_ssd_params& p) {
   const int64_t nchunks = ceil_div(p.seqlen, p.chunk_size);
   const size_t per = (size_t)p.batch * nchunks * p.nheads * p.chunk_size * sizeof(float);
-  return 2 * ((per + 255) & ~(size_t)255);
+  return 2 * ((per + 255) & ~(size_t)255) + (((size_t)p.batch * p.nheads * sizeof(int)) + 255 & ~(size_t)255);
 }
 
 int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
@@ -639,7 +809,15 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
   };
   int lrc;
   const bool dfold = !p.d_has_hdim;          // scalar-per-head D (or no D): fold into M's diagonal
-  if (p.mode != TV_SSD_FULL) lrc = launch(ssd_fused_kernel<false, false, true>);
+  if (p.mode != TV_SSD_FULL) {
+    int* first_chunk = (int*)((char*)workspace + 2 * per);
+    const int BH = p.batch * p.nheads;
+    ssd_suffix_scan_kernel<<<(BH + 3) / 4, 128, 0, s>>>(cs, p.logdecay_sum, first_chunk, BH, p.nheads, nchunks, Q);
+    TV_CUDA_OK(cudaGetLastError());
+    TV_CUDA_OK(cudaFuncSetAttribute(ssd_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st::SMEM_BYTES));
+    ssd_state_kernel<<<grid, st::THREADS, st::SMEM_BYTES, s>>>(maps, a, first_chunk);
+    lrc = TV_OK;
+  }
   else if (p.z != nullptr) lrc = dfold ? launch(ssd_fused_kernel<true, true, true>) : launch(ssd_fused_kernel<true, true, false>);
   else lrc = dfold ? launch(ssd_fused_kernel<true, false, true>) : launch(ssd_fused_kernel<true, false, false>);
   if (lrc != TV_OK) return lrc;

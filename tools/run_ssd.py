@@ -20,3 +20,14 @@ for _ in range(iters):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 print(f"L={L} H={H} G={G} ssd {ms:.3f} ms  {(45312/128*H)*L/ms/1e6:.1f} GB/s  {ms*1e3/ (L/128):.2f} us/chunk")
+# shard summary (pass 1 of the sequence-sharded path)
+for scale, tag in ((1.0, "fast decay (A = -1..-H)"), (1e-4, "slow decay (A * 1e-4: every chunk contributes)")):
+    A2 = A * scale
+    for _ in range(2):
+        tv.mamba_chunk_state_summary(x, dt, A2, B, 128, dt_bias=dt_bias, dt_softplus=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        tv.mamba_chunk_state_summary(x, dt, A2, B, 128, dt_bias=dt_bias, dt_softplus=True)
+    e1.record(); torch.cuda.synchronize()
+    print(f"  state summary, {tag}: {e0.elapsed_time(e1) / iters:.3f} ms")
