@@ -116,6 +116,8 @@ typedef struct {
   int32_t dtype;               /* tv_dtype of x / dt / B / C / z / out                           */
   int32_t mode;                /* tv_ssd_mode                                                    */
   int32_t force_simt;          /* 1: use the fp32 CUDA-core kernels even where a tcgen05 kernel exists */
+  int32_t reuse_dt_cumsum;     /* 1: `workspace` still holds dt/cumsum of the previous call with the same dt, A, dt_bias,
+                                  dims and kernel family (pass 2 of the sharded path right after pass 1): skip stage (i) */
 } tv_ssd_params;
 
 /* Bytes of caller-allocated scratch tv_ssd_chunk_scan_fwd needs for these dims (0 is possible). */

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header_sizes():
     import timeviper_b200._lib as L
     assert ctypes.sizeof(L.ConvParams) == 6 * 8 + 4 * 4 + 4 * 8 + 2 * 4
     assert ctypes.sizeof(L.RmsnormParams) == 5 * 8 + 8 + 2 * 4 + 3 * 8 + 3 * 4 + 4   # + tail padding
-    assert ctypes.sizeof(L.SsdParams) == 12 * 8 + 7 * 4 + 4 + 15 * 8 + 2 * 4 + 2 * 4 + 3 * 4 + 4
+    assert ctypes.sizeof(L.SsdParams) == 12 * 8 + 7 * 4 + 4 + 15 * 8 + 2 * 4 + 2 * 4 + 4 * 4
 
 
 def test_null_and_invalid_arguments_return_error_codes_without_touching_a_gpu():

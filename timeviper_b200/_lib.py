@@ -42,7 +42,7 @@ class SsdParams(C.Structure):
                 ("z_batch_stride", C.c_int64), ("z_seq_stride", C.c_int64), ("z_head_stride", C.c_int64),
                 ("d_has_hdim", C.c_int32), ("dt_softplus", C.c_int32),
                 ("dt_min", C.c_float), ("dt_max", C.c_float),
-                ("dtype", C.c_int32), ("mode", C.c_int32), ("force_simt", C.c_int32)]
+                ("dtype", C.c_int32), ("mode", C.c_int32), ("force_simt", C.c_int32), ("reuse_dt_cumsum", C.c_int32)]
 
 
 EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd",

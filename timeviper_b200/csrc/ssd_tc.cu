@@ -609,10 +609,12 @@ ssd_suffix_scan_kernel(const float* __restrict__ cs, float* __restrict__ logdeca
 
 namespace st {
 constexpr int THREADS = 192;                     // warps 0-3: x scaling, warp 4: TMA producer, warp 5: MMA issuer
-constexpr uint32_t OFF_B = 0, OFF_X = 2 * tc::TILE_BC, OFF_XS = OFF_X + 2 * tc::XSTAGE;
+constexpr int NST = 3;                            // B / x stages: TMA latency (~2000 cycles) x 54 KB per chunk needs depth
+constexpr uint32_t OFF_B = 0, OFF_X = NST * tc::TILE_BC, OFF_XS = OFF_X + NST * tc::XSTAGE;
 constexpr uint32_t OFF_BAR = OFF_XS + 2 * tc::TILE_X;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;
-enum Bar { FULL0 = 0, FULL1, EMPTY0, EMPTY1, XSFULL0, XSFULL1, XSEMPTY0, XSEMPTY1, DONE, NBAR };
+enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NST, XSFULL0 = EMPTY0 + NST, XSEMPTY0 = XSFULL0 + 2, DONE = XSEMPTY0 + 2, NBAR };
+static_assert(OFF_X % 1024 == 0 && SMEM_BYTES <= kMaxDynSmem, "state kernel smem");
 static_assert(OFF_XS % 1024 == 0, "tile alignment");
 }  // namespace st
 
@@ -630,10 +632,10 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
   const int c_first = first_chunk[(int64_t)b * a.H + h];
   const int count = n - c_first;                       // chunks n-1, n-2, ..., c_first
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < st::NST; ++i) {
       mbar_init(&bars[st::FULL0 + i], 1); mbar_init(&bars[st::EMPTY0 + i], 5);      // 4 scaling warps + the MMA commit
-      mbar_init(&bars[st::XSFULL0 + i], 4); mbar_init(&bars[st::XSEMPTY0 + i], 1);
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[st::XSFULL0 + i], 4); mbar_init(&bars[st::XSEMPTY0 + i], 1); }
     mbar_init(&bars[st::DONE], 1);
     fence_mbar_init();
   }
@@ -648,8 +650,8 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
     if (elect_one()) {
       prefetch_tmap(&maps.x); prefetch_tmap(&maps.b);
       for (int i = 0; i < count; ++i) {
-        const int c = n - 1 - i, s = i & 1, u = i >> 1;
-        if (i >= 2) mbar_wait(&bars[st::EMPTY0 + s], (u - 1) & 1);
+        const int c = n - 1 - i, s = i % st::NST, u = i / st::NST;
+        if (i >= st::NST) mbar_wait(&bars[st::EMPTY0 + s], (u - 1) & 1);
         uint8_t* sb = smem + st::OFF_B + s * TILE_BC;
         uint8_t* sx = smem + st::OFF_X + s * XSTAGE;
         mbar_arrive_expect_tx(&bars[st::FULL0 + s], TILE_BC + XSTAGE);
@@ -670,17 +672,17 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
       const uint64_t dXS = umma_smem_desc(sbase + st::OFF_XS, 4096, 256, SWZ_32B);
 #pragma unroll 1
       for (int i = 0; i < count; ++i) {
-        const int s = i & 1, u = i >> 1;
+        const int s = i % st::NST, u = i / st::NST, xb = i & 1, xu = i >> 1;
         mbar_wait(&bars[st::FULL0 + s], u & 1);
-        mbar_wait(&bars[st::XSFULL0 + s], u & 1);
+        mbar_wait(&bars[st::XSFULL0 + xb], xu & 1);
         tc_fence_after();
         const uint64_t db = umma_desc_advance(dB, (uint32_t)(s * (TILE_BC >> 4)));
-        const uint64_t dx = umma_desc_advance(dXS, (uint32_t)(s * (TILE_X >> 4)));
+        const uint64_t dx = umma_desc_advance(dXS, (uint32_t)(xb * (TILE_X >> 4)));
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           umma_ss(tmem, umma_desc_advance(db, j * 128), umma_desc_advance(dx, j * 32), ID_ST, (i > 0 || j > 0) ? 1u : 0u);
         umma_commit(&bars[st::EMPTY0 + s]);
-        umma_commit(&bars[st::XSEMPTY0 + s]);
+        umma_commit(&bars[st::XSEMPTY0 + xb]);
       }
       umma_commit(&bars[st::DONE]);
     }
@@ -689,7 +691,7 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
     const int r = threadIdx.x;
     float T = 0.f;
     for (int i = 0; i < count; ++i) {
-      const int s = i & 1, u = i >> 1;
+      const int s = i % st::NST, u = i / st::NST, xb = i & 1, xu = i >> 1;
       const uint8_t* xst = smem + st::OFF_X + s * XSTAGE;
       const float* sCS = reinterpret_cast<const float*>(xst + TILE_X);
       const float* sDT = sCS + 128;
@@ -698,8 +700,8 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
       const float w_r = sDT[r] * __expf(cs_last - sCS[r] + T);
       T += cs_last;
       const __nv_bfloat162 w2 = __float2bfloat162_rn(w_r);
-      if (i >= 2) mbar_wait(&bars[st::XSEMPTY0 + s], (u - 1) & 1);
-      uint8_t* xs_out = smem + st::OFF_XS + s * TILE_X;
+      if (i >= 2) mbar_wait(&bars[st::XSEMPTY0 + xb], (xu - 1) & 1);
+      uint8_t* xs_out = smem + st::OFF_XS + xb * TILE_X;
 #pragma unroll
       for (int q = 0; q < 10; ++q) {
         uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, q));
@@ -710,7 +712,7 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&bars[st::XSFULL0 + s]); mbar_arrive(&bars[st::EMPTY0 + s]); }
+      if (lane == 0) { mbar_arrive(&bars[st::XSFULL0 + xb]); mbar_arrive(&bars[st::EMPTY0 + s]); }
     }
     mbar_wait(&bars[st::DONE], 0);
     tc_fence_after();
@@ -759,8 +761,10 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
   const size_t per = (((size_t)p.batch * nchunks * p.nheads * Q * sizeof(float)) + 255) & ~(size_t)255;
   float* dt_act = (float*)workspace;
   float* cs = (float*)((char*)workspace + per);
-  int rc = launch_dt_cumsum(p, dt_act, cs, s);
-  if (rc != TV_OK) return rc;
+  if (!p.reuse_dt_cumsum) {
+    int rc = launch_dt_cumsum(p, dt_act, cs, s);
+    if (rc != TV_OK) return rc;
+  }
 
   Maps maps;
   const uint64_t L = (uint64_t)p.seqlen;

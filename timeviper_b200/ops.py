@@ -135,7 +135,7 @@ def _workspace(nbytes, device):
 
 
 def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_softplus, dt_limit, mode,
-              force_simt=False, want_final=True, want_logdecay=False):
+              force_simt=False, want_final=True, want_logdecay=False, reuse_dt_cumsum=False):
     batch, seqlen, nheads, headdim = x.shape
     ngroups, dstate = B.shape[2], B.shape[3]
     assert nheads % ngroups == 0
@@ -192,7 +192,7 @@ def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_sof
         z_head_stride=0 if z is None else z.stride(2),
         d_has_hdim=int(D is not None and D.dim() == 2), dt_softplus=int(bool(dt_softplus)),
         dt_min=lo, dt_max=hi if math.isfinite(hi) else float("inf"), dtype=code, mode=mode,
-        force_simt=int(bool(force_simt)))
+        force_simt=int(bool(force_simt)), reuse_dt_cumsum=int(bool(reuse_dt_cumsum)))
     lib = L.load()
     need = lib.tv_ssd_workspace_bytes(C.byref(p))
     ws = _workspace(need, dev)
@@ -202,7 +202,8 @@ def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_sof
 
 def mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initial_states=None,
                               seq_idx=None, cu_seqlens=None, dt_softplus=False, dt_limit=(0.0, float("inf")),
-                              return_final_states=False, return_varlen_states=False, _force_simt=False):
+                              return_final_states=False, return_varlen_states=False, _force_simt=False,
+                              _reuse_dt_cumsum=False):
     """
     Argument:
         x: (batch, seqlen, nheads, headdim)        dt: (batch, seqlen, nheads)       A: (nheads)
@@ -215,7 +216,8 @@ def mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bia
         raise NotImplementedError("mamba_chunk_scan_combined: seq_idx / cu_seqlens / varlen states are "
                                   "outside the prefill path (the reference passes seq_idx=None)")
     out, fin, _ = _ssd_call(x, dt, A, B, C, chunk_size, D, z, dt_bias, initial_states, dt_softplus, dt_limit,
-                            L.TV_SSD_FULL, force_simt=_force_simt, want_final=return_final_states)
+                            L.TV_SSD_FULL, force_simt=_force_simt, want_final=return_final_states,
+                            reuse_dt_cumsum=_reuse_dt_cumsum)
     return (out, fin) if return_final_states else out
 
 

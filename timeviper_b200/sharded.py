@@ -58,11 +58,12 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
     logP_all = gathered[..., -1]
     S_in = ops.fold_boundary_states(S_all, logP_all, rank) if rank > 0 else None
 
-    # 5. full local scan from the folded entering state
+    # 5. full local scan from the folded entering state (dt/cumsum of pass 1 is still in the op's workspace)
+    reuse = {"_reuse_dt_cumsum": True} if ops is _cuda_ops else {}
     y, ssm_state = ops.mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size=mixer.chunk_size, D=mixer.D, z=None,
                                                  dt_bias=mixer.dt_bias, dt_softplus=True,
                                                  dt_limit=mixer.time_step_limit, initial_states=S_in,
-                                                 return_final_states=True)
+                                                 return_final_states=True, **reuse)
     if cache_params is not None and rank == world - 1:
         xt = xBC.transpose(1, 2)
         conv_states = nn.functional.pad(xt, (cache_params.conv_kernel_size - xt.shape[-1], 0))

@@ -1,0 +1,28 @@
+"""torchrun helper: per-kernel CUDA time of one sharded scan_core step (rank 0 prints the table)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from torch.profiler import profile, ProfilerActivity
+import timeviper_b200 as tv
+from oracle import mamba2_ref as R
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+cfg = tv.Mamba2Config.nanov2_9b()
+L = int(sys.argv[1]) // world if len(sys.argv) > 1 else 131072 // world
+p = R.nemotron_random_params(cfg.hidden_size, cfg.mamba_num_heads, cfg.mamba_head_dim, cfg.n_groups, cfg.ssm_state_size, nondegenerate=False)
+mixer = tv.Mamba2MixerPrefill(cfg).to(torch.bfloat16).cuda()
+mixer.load_state_dict({k: v.to(torch.bfloat16) for k, v in p.items()})
+proj = (torch.randn(1, L, cfg.projection_size, device="cuda") * 0.5).to(torch.bfloat16)
+with torch.no_grad():
+    for _ in range(5):
+        tv.sharded_scan_core(mixer, proj)
+    torch.cuda.synchronize(); dist.barrier()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(10):
+            tv.sharded_scan_core(mixer, proj)
+        torch.cuda.synchronize()
+if rank == 0:
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+dist.destroy_process_group()
