@@ -42,30 +42,36 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
   x += (int64_t)b * xbs + c0;
   out += (int64_t)b * obs + c0;
 
+  // All arithmetic is done on float2 pairs (FFMA2 / FMUL2 / FADD2, sm_100): the kernel is issue-bound next to the
+  // memory system (two MUFU + ~10 scalar instructions per element), and the packed forms halve the FP issue slots.
+  constexpr int V2 = V / 2;
   // weights (dim, K) row-major: this thread's V*K values are contiguous
-  float w[K][V], bv[V];
+  float2 w[K][V2], bv[V2];
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
+  for (int v = 0; v < V2; ++v) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) w[k][v] = to_f32<T>(weight[(int64_t)(c0 + v) * K + k]);
-    bv[v] = bias != nullptr ? to_f32<T>(bias[c0 + v]) : 0.f;
+    for (int k = 0; k < K; ++k)
+      w[k][v] = make_float2(to_f32<T>(weight[(int64_t)(c0 + 2 * v) * K + k]), to_f32<T>(weight[(int64_t)(c0 + 2 * v + 1) * K + k]));
+    bv[v] = bias != nullptr ? make_float2(to_f32<T>(bias[c0 + 2 * v]), to_f32<T>(bias[c0 + 2 * v + 1])) : make_float2(0.f, 0.f);
   }
 
   // the K-1 rows preceding t0
-  float win[K - 1][V];
+  float2 win[K - 1][V2];
 #pragma unroll
   for (int j = 0; j < K - 1; ++j) {
     const int t = t0 - (K - 1) + j;
+    float tmp[V];
     if (t >= 0) {
-      Raw4<T> r; r.load(x + (int64_t)t * xss); r.unpack(win[j]);
+      Raw4<T> r; r.load(x + (int64_t)t * xss); r.unpack(tmp);
     } else if (init != nullptr) {  // (b, dim, K-1): column t+(K-1) of the carried-in state
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        win[j][v] = to_f32<T>(init[((int64_t)b * dim + c0 + v) * (K - 1) + (t + K - 1)]);
+      for (int v = 0; v < V; ++v) tmp[v] = to_f32<T>(init[((int64_t)b * dim + c0 + v) * (K - 1) + (t + K - 1)]);
     } else {
 #pragma unroll
-      for (int v = 0; v < V; ++v) win[j][v] = 0.f;
+      for (int v = 0; v < V; ++v) tmp[v] = 0.f;
     }
+#pragma unroll
+    for (int v = 0; v < V2; ++v) win[j][v] = make_float2(tmp[2 * v], tmp[2 * v + 1]);
   }
 
   for (int tt = t0; tt < t1; tt += CONV_U) {
@@ -76,23 +82,30 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
 #pragma unroll
     for (int u = 0; u < CONV_U; ++u) {
       if (tt + u < t1) {
-        float xv[V], o[V];
-        xin[u].unpack(xv);
+        float xf[V], o[V];
+        xin[u].unpack(xf);
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          float acc = bv[v];
+        for (int v = 0; v < V2; ++v) {
+          const float2 xv = make_float2(xf[2 * v], xf[2 * v + 1]);
+          float2 acc = bv[v];
 #pragma unroll
-          for (int k = 0; k < K - 1; ++k) acc = fmaf(w[k][v], win[k][v], acc);
-          acc = fmaf(w[K - 1][v], xv[v], acc);
-          o[v] = SILU ? silu<FAST>(acc) : acc;
+          for (int k = 0; k < K - 1; ++k) acc = __ffma2_rn(w[k][v], win[k][v], acc);
+          acc = __ffma2_rn(w[K - 1][v], xv, acc);
+          if (SILU) {
+            if (FAST) {    // x / (1 + 2^(-x log2 e)) with packed scale / add / multiply around the two MUFU pairs
+              const float2 tneg = __fmul2_rn(acc, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+              const float2 d = __fadd2_rn(make_float2(ex2_approx_f(tneg.x), ex2_approx_f(tneg.y)), make_float2(1.f, 1.f));
+              acc = __fmul2_rn(acc, make_float2(rcp_approx_f(d.x), rcp_approx_f(d.y)));
+            } else {
+              acc = make_float2(silu<false>(acc.x), silu<false>(acc.y));
+            }
+          }
+          o[2 * v] = acc.x; o[2 * v + 1] = acc.y;
+#pragma unroll
+          for (int k = 0; k < K - 2; ++k) win[k][v] = win[k + 1][v];
+          win[K - 2][v] = xv;
         }
         Raw4<T>::store(out + (int64_t)(tt + u) * oss, o);
-#pragma unroll
-        for (int k = 0; k < K - 2; ++k)
-#pragma unroll
-          for (int v = 0; v < V; ++v) win[k][v] = win[k + 1][v];
-#pragma unroll
-        for (int v = 0; v < V; ++v) win[K - 2][v] = xv[v];
       }
     }
   }
@@ -103,7 +116,7 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
     for (int v = 0; v < V; ++v)
 #pragma unroll
       for (int j = 0; j < K - 1; ++j)
-        fin[((int64_t)b * dim + c0 + v) * (K - 1) + j] = from_f32<T>(win[j][v]);
+        fin[((int64_t)b * dim + c0 + v) * (K - 1) + j] = from_f32<T>((v & 1) ? win[j][v >> 1].y : win[j][v >> 1].x);
   }
 }
 

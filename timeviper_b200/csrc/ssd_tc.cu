@@ -88,24 +88,27 @@ __device__ __forceinline__ void m_block(uint32_t t_src, uint32_t t_dst, const fl
                                         int lane, float Dh, bool diag) {
   uint32_t r[32];
   tmem_ld32(t_src, r);
-  float e[32];
+  float2 e[16];                                  // packed pairs: FADD2 / FMUL2 halve the FP issue slots
+  const float2 Em2 = make_float2(Em, Em);
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 f4 = *reinterpret_cast<const float4*>(sFk + j);
-    e[j] = Em + f4.x; e[j + 1] = Em + f4.y; e[j + 2] = Em + f4.z; e[j + 3] = Em + f4.w;
+  for (int j = 0; j < 16; j += 2) {
+    const float4 f4 = *reinterpret_cast<const float4*>(sFk + 2 * j);
+    e[j] = __fadd2_rn(Em2, make_float2(f4.x, f4.y));
+    e[j + 1] = __fadd2_rn(Em2, make_float2(f4.z, f4.w));
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) e[j] = ex2_approx(e[j]);
+  for (int j = 0; j < 16; ++j) e[j] = make_float2(ex2_approx(e[j].x), ex2_approx(e[j].y));
   tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    e[j] *= __uint_as_float(r[j]);
-    if (diag && j > lane) e[j] = 0.f;                   // causal mask (diagonal block only)
-    if (DFOLD && diag && j == lane) e[j] += Dh;         // D skip folded into the diagonal
-  }
   uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(e[2 * j], e[2 * j + 1]);
+  for (int j = 0; j < 16; ++j) {
+    float2 v = __fmul2_rn(e[j], make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+    if (diag && 2 * j > lane) v.x = 0.f;                   // causal mask (diagonal block only)
+    if (diag && 2 * j + 1 > lane) v.y = 0.f;
+    if (DFOLD && diag && 2 * j == lane) v.x += Dh;         // D skip folded into the diagonal
+    if (DFOLD && diag && 2 * j + 1 == lane) v.y += Dh;
+    pk[j] = pack_bf16x2(v.x, v.y);
+  }
   tmem_st16(t_dst, pk);
 }
 
@@ -116,17 +119,21 @@ __device__ __forceinline__ void m_block(uint32_t t_src, uint32_t t_dst, const fl
 __device__ __forceinline__ void m_block_offdiag(uint32_t t_src, uint32_t t_dst, const float* __restrict__ sVk, float um) {
   uint32_t r[32];
   tmem_ld32(t_src, r);
-  float e[32];
+  float2 e[16];
+  const float2 um2 = make_float2(um, um);
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 v4 = *reinterpret_cast<const float4*>(sVk + j);
-    e[j] = v4.x * um; e[j + 1] = v4.y * um; e[j + 2] = v4.z * um; e[j + 3] = v4.w * um;
+  for (int j = 0; j < 16; j += 2) {
+    const float4 v4 = *reinterpret_cast<const float4*>(sVk + 2 * j);
+    e[j] = __fmul2_rn(make_float2(v4.x, v4.y), um2);
+    e[j + 1] = __fmul2_rn(make_float2(v4.z, v4.w), um2);
   }
   tmem_ld_wait();
   uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    pk[j] = pack_bf16x2(e[2 * j] * __uint_as_float(r[2 * j]), e[2 * j + 1] * __uint_as_float(r[2 * j + 1]));
+  for (int j = 0; j < 16; ++j) {
+    const float2 v = __fmul2_rn(e[j], make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+    pk[j] = pack_bf16x2(v.x, v.y);
+  }
   tmem_st16(t_dst, pk);
 }
 
@@ -437,8 +444,11 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
             }
         }
 #pragma unroll
-        for (int j = 0; j < 48; ++j)
-          if (j < nc * 16) v[j] = __float_as_uint(__uint_as_float(v[j]) * a_c);
+        for (int j = 0; j < 48; j += 2)
+          if (j < nc * 16) {
+            const float2 d2 = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(a_c, a_c));
+            v[j] = __float_as_uint(d2.x); v[j + 1] = __float_as_uint(d2.y);
+          }
 #pragma unroll
         for (int pc = 0; pc < 3; ++pc)
           if (pc < nc) tmem_st16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
@@ -519,8 +529,9 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float y0 = fmaf(e_r, __uint_as_float(yo[2 * j]), __uint_as_float(yd[2 * j]));
-            float y1 = fmaf(e_r, __uint_as_float(yo[2 * j + 1]), __uint_as_float(yd[2 * j + 1]));
+            const float2 y2 = __ffma2_rn(make_float2(e_r, e_r), make_float2(__uint_as_float(yo[2 * j]), __uint_as_float(yo[2 * j + 1])),
+                                         make_float2(__uint_as_float(yd[2 * j]), __uint_as_float(yd[2 * j + 1])));
+            float y0 = y2.x, y1 = y2.y;
             if (!DFOLD) { y0 += xv[2 * j]; y1 += xv[2 * j + 1]; }
             if (HAS_Z) { y0 *= zv[2 * j]; y1 *= zv[2 * j + 1]; }
             pk[j] = pack_bf16x2(y0, y1);
