@@ -253,3 +253,32 @@ def test_mixer_bf16_9b_dims_vs_oracle(tv):
     nr = R.gated_rmsnorm_ref(yr, pc["norm.weight"], None, gate, 1e-5, H * P // G, False)
     assert relerr(y, nr) < 2e-2
     assert relerr(ssm, sr) < 2e-2
+
+
+def test_streamed_prefill_from_host_equals_forward(tv):
+    """prefill_from_host (segments streamed over three CUDA streams, states carried between segments) must equal
+    the one-shot forward, including the cache side effects -- also with a ragged last segment."""
+    torch.manual_seed(77)
+    cfg = tv.Mamba2Config(hidden_size=256, mamba_num_heads=16, mamba_head_dim=80, n_groups=2, ssm_state_size=128,
+                          chunk_size=128)
+    mixer = tv.Mamba2MixerPrefill(cfg)
+    mixer.reset_parameters_like_reference()
+    with torch.no_grad():
+        mixer.A_log.copy_(torch.log(torch.rand(16) * 0.05 + 0.002))
+    mixer = mixer.to(torch.bfloat16).cuda()
+    L = 5 * 256 + 77
+    hs = torch.randn(1, L, 256).to(torch.bfloat16).pin_memory()
+
+    class Cache:
+        conv_kernel_size = 4
+        def update_conv_state(self, layer_idx, new_conv_state, cache_init=False): self.conv = new_conv_state
+        def update_ssm_state(self, layer_idx, new_ssm_state): self.ssm = new_ssm_state
+    c1, c2 = Cache(), Cache()
+    with torch.no_grad():
+        ref = mixer(hs.cuda(), cache_params=c1)
+        out = mixer.prefill_from_host(hs, segment_tokens=256, cache_params=c2)
+    torch.cuda.synchronize()
+    assert out.is_pinned() and out.shape == (1, L, 256)
+    assert relerr(out, ref) < 2e-2
+    assert relerr(c2.ssm, c1.ssm) < 2e-2
+    assert torch.equal(c2.conv, c1.conv)

@@ -76,8 +76,9 @@ class Mamba2MixerPrefill(nn.Module):
 
     # -- the three-kernel core, on an already projected input (what bench.py's `value` times) ------------
     def scan_core(self, projected_states, cache_params=None, conv_initial_states=None, ssm_initial_states=None,
-                  return_states=False):
-        """projected_states (b, L, d_inner + conv_dim + H) -> normed scan output (b, L, d_inner)."""
+                  return_states=False, return_conv_state=False):
+        """projected_states (b, L, d_inner + conv_dim + H) -> normed scan output (b, L, d_inner).
+        With return_states: (y, ssm_state[, conv_final_states (b, conv_dim, K-1)])."""
         batch_size, seq_len, _ = projected_states.shape
         gts = self.n_groups * self.ssm_state_size
         gate, hidden_states_B_C, dt = projected_states.split(
@@ -86,9 +87,13 @@ class Mamba2MixerPrefill(nn.Module):
             xt = hidden_states_B_C.transpose(1, 2)
             conv_states = nn.functional.pad(xt, (cache_params.conv_kernel_size - xt.shape[-1], 0))
             cache_params.update_conv_state(layer_idx=self.layer_idx, new_conv_state=conv_states, cache_init=True)
-        hidden_states_B_C = ops.causal_conv1d_fn(                               # :619-624
+        conv_out = ops.causal_conv1d_fn(                                        # :619-624
             x=hidden_states_B_C.transpose(1, 2), weight=self.conv1d.weight.squeeze(1), bias=self.conv1d.bias,
-            initial_states=conv_initial_states, activation=self.activation).transpose(1, 2)
+            initial_states=conv_initial_states, return_final_states=return_conv_state, activation=self.activation)
+        conv_final = None
+        if return_conv_state:
+            conv_out, conv_final = conv_out
+        hidden_states_B_C = conv_out.transpose(1, 2)
         hidden_states, B, C = torch.split(hidden_states_B_C, [self.intermediate_size, gts, gts], dim=-1)
         A = -torch.exp(self.A_log.float())                                      # :550-552
         scan_output, ssm_state = ops.mamba_chunk_scan_combined(                 # :639-653
@@ -101,7 +106,71 @@ class Mamba2MixerPrefill(nn.Module):
             cache_params.update_ssm_state(layer_idx=self.layer_idx, new_ssm_state=ssm_state)
         scan_output = scan_output.view(batch_size, seq_len, -1)
         scan_output = self.norm(scan_output, gate)                              # :664
-        return (scan_output, ssm_state) if return_states else scan_output
+        if return_states:
+            return (scan_output, ssm_state, conv_final) if return_conv_state else (scan_output, ssm_state)
+        return scan_output
+
+    @torch.no_grad()
+    def prefill_from_host(self, hidden_host, out_host=None, segment_tokens=16384, cache_params=None):
+        """Prefill a (b, L, hidden) sequence that lives in (pinned) HOST memory and return the mixer output in
+        pinned host memory.  The sequence is streamed through the GPU in segments: the H2D copy of segment i+1, the
+        mixer on segment i (in_proj -> conv -> SSD -> norm -> out_proj, continued from the carried conv/SSM
+        states) and the D2H copy of segment i-1 run on three streams, so PCIe and compute overlap instead of adding
+        up.  Same result as ``forward`` on the whole sequence (the carried states are the ones ``forward`` returns:
+        conv halo of K-1 columns through ``initial_states`` of causal_conv1d_fn, SSM state through
+        ``initial_states`` of mamba_chunk_scan_combined); same cache side effects."""
+        dev = self.in_proj.weight.device
+        b, L, hidden = hidden_host.shape
+        seg = max(self.chunk_size, (int(segment_tokens) // self.chunk_size) * self.chunk_size)
+        if out_host is None:
+            out_host = torch.empty((b, L, self.hidden_size), dtype=hidden_host.dtype).pin_memory()
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        nseg = (L + seg - 1) // seg
+        d_in = [torch.empty((b, seg, hidden), dtype=hidden_host.dtype, device=dev) for _ in range(2)]
+        d_out = [torch.empty((b, seg, self.hidden_size), dtype=hidden_host.dtype, device=dev) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(nseg)]
+        ev_cmp = [torch.cuda.Event() for _ in range(nseg)]
+        ev_out = [torch.cuda.Event() for _ in range(nseg)]
+        conv_state, ssm_state, tail = None, None, None
+        K = self.conv_kernel_size
+        for i in range(nseg):
+            t0, t1 = i * seg, min((i + 1) * seg, L)
+            n = t1 - t0
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_cmp[i - 2])                # the compute stream is done reading this buffer
+                d_in[i % 2][:, :n].copy_(hidden_host[:, t0:t1], non_blocking=True)
+                ev_in[i].record(s_in)
+            cur.wait_event(ev_in[i])
+            if i >= 2:
+                cur.wait_event(ev_out[i - 2])                     # the D2H copy has drained this output buffer
+            proj = self.in_proj(d_in[i % 2][:, :n])
+            y, ssm_state, conv_state = self.scan_core(proj, conv_initial_states=conv_state,
+                                                      ssm_initial_states=ssm_state, return_states=True,
+                                                      return_conv_state=True)
+            if cache_params is not None:                           # last K pre-conv columns of the whole sequence
+                xBC = proj[..., self.intermediate_size:self.intermediate_size + self.conv_dim]
+                seg_tail = xBC[:, max(0, n - K):].transpose(1, 2)
+                tail = seg_tail if tail is None else torch.cat([tail, seg_tail], dim=-1)[..., -K:]
+                tail = tail.contiguous()
+            torch.matmul(y, self.out_proj.weight.t(), out=d_out[i % 2][:, :n])
+            if self.out_proj.bias is not None:
+                d_out[i % 2][:, :n].add_(self.out_proj.bias)
+            ev_cmp[i].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[i])
+                out_host[:, t0:t1].copy_(d_out[i % 2][:, :n], non_blocking=True)
+                ev_out[i].record(s_out)
+        cur.wait_stream(s_out)
+        if cache_params is not None:
+            cache_params.update_conv_state(layer_idx=self.layer_idx,
+                                           new_conv_state=nn.functional.pad(tail, (K - tail.shape[-1], 0)),
+                                           cache_init=True)
+            cache_params.update_ssm_state(layer_idx=self.layer_idx, new_ssm_state=ssm_state)
+        return out_host
 
     def forward(self, hidden_states, cache_params=None, cache_position=None, attention_mask=None, seq_idx=None):
         if not hidden_states.is_cuda:
