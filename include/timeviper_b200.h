@@ -140,6 +140,9 @@ int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, cons
 /* Debug hook (profiling only): device buffer of nchunks*16 int64 that CTA (0,0) of the fused SSD kernel fills
  * with clock64() stamps of its pipeline events; NULL (default) disables it. */
 void tv_debug_set_trace(void* device_buffer);
+/* Profiling builds only (python -m timeviper_b200.build --trace): bitmask of per-role work the fused SSD kernel skips,
+ * to find the critical path by ablation (results are then wrong by construction).  No effect in normal builds. */
+void tv_debug_set_ablate(int mask);
 
 #ifdef __cplusplus
 }

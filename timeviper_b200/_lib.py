@@ -47,7 +47,7 @@ class SsdParams(C.Structure):
 
 EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd",
            "tv_ssd_workspace_bytes", "tv_ssd_chunk_scan_fwd", "tv_ssd_kernel_family",
-           "tv_ssd_fold_boundary_states", "tv_debug_set_trace")
+           "tv_ssd_fold_boundary_states", "tv_debug_set_trace", "tv_debug_set_ablate")
 
 _lib = None
 
@@ -78,6 +78,8 @@ def load():
     lib.tv_ssd_fold_boundary_states.restype = C.c_int
     lib.tv_debug_set_trace.argtypes = [C.c_void_p]
     lib.tv_debug_set_trace.restype = None
+    lib.tv_debug_set_ablate.argtypes = [C.c_int]
+    lib.tv_debug_set_ablate.restype = None
     if lib.tv_abi_version() != 1:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.tv_abi_version()} != 1")
     _lib = lib

@@ -66,3 +66,4 @@ extern "C" int tv_ssd_chunk_scan_fwd(const tv_ssd_params* p, void* workspace, si
 
 // Debug hook (not part of the reference-facing ABI): per-chunk clock64 stamps of CTA (0,0) of the fused SSD kernel.
 extern "C" void tv_debug_set_trace(void* device_buffer) { tv::set_trace_buffer(device_buffer); }
+extern "C" void tv_debug_set_ablate(int mask) { tv::set_ablate(mask); }

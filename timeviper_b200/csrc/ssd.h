@@ -21,6 +21,7 @@ bool tc_supported(const tv_ssd_params& p);
 size_t tc_workspace_bytes(const tv_ssd_params& p);
 int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s);
 void set_trace_buffer(void* p);
+void set_ablate(int mask);
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
 

@@ -59,6 +59,7 @@ struct Args {
   int L, H, G, nchunks, d_has_hdim;
   int64_t zbs, zss, zhs;
   long long* trace;                                // optional: per-chunk clock64 stamps of CTA (0,0), 16 per chunk
+  int ablate;                                      // profiling only (TV_ENABLE_TRACE builds): bitmask of work to skip
 };
 
 #ifdef TV_ENABLE_TRACE   // profiling builds only (python timeviper_b200/build.py --trace): keeps the hot loops small
@@ -68,6 +69,13 @@ struct Args {
   } while (0)
 #else
 #define TV_TRACE(ev, c) do { } while (0)
+#endif
+// Ablation switches (profiling builds only): tools/ablate_ssd.py times the kernel with parts of the work skipped
+// to find the critical path; in normal builds TV_ABLATE() is the constant 0 and the branches vanish.
+#ifdef TV_ENABLE_TRACE
+#define TV_ABLATE(bit) ((a.ablate >> (bit)) & 1)
+#else
+#define TV_ABLATE(bit) 0
 #endif
 __device__ __forceinline__ uint32_t off_sw32(int r, int q) {  // row r, 16-byte chunk q (8 p each) of a [128][80] tile
   return (uint32_t)(q >> 1) * 4096u + (uint32_t)r * 32u + (uint32_t)(((q & 1) ^ ((r >> 2) & 1)) << 4);
@@ -200,7 +208,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       for (int c = 0; c < n; ++c) {
         const int s = c & 1, u = c >> 1;
         const int t0 = c * Q;
-        if (c + PF < n) l2_prefetch(c + PF);
+        if (c + PF < n && !TV_ABLATE(10)) l2_prefetch(c + PF);
         if (c >= 2) mbar_wait(&bars[EMPTYB0 + s], (u - 1) & 1);
         TV_TRACE(0, c);
 #ifdef TV_ENABLE_TRACE
@@ -210,19 +218,24 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           a.trace[(int64_t)c * 16 + 15] = (long long)gt;
         }
 #endif
+        if (TV_ABLATE(9)) mbar_arrive(&bars[FULLB0 + s]); else {
         mbar_arrive_expect_tx(&bars[FULLB0 + s], TILE_BC);
         tma_load_4d(smem + OFF_B + s * TILE_BC, &maps.b, &bars[FULLB0 + s], 0, g, t0, b);
         tma_load_4d(smem + OFF_B + s * TILE_BC + 16384, &maps.b, &bars[FULLB0 + s], 64, g, t0, b);
+        }
         if (FULL) {
           if (c >= 2) mbar_wait(&bars[EMPTYC0 + s], (u - 1) & 1);
+          if (TV_ABLATE(9)) mbar_arrive(&bars[FULLC0 + s]); else {
           mbar_arrive_expect_tx(&bars[FULLC0 + s], TILE_BC);
           tma_load_4d(smem + OFF_C + s * TILE_BC, &maps.c, &bars[FULLC0 + s], 0, g, t0, b);
           tma_load_4d(smem + OFF_C + s * TILE_BC + 16384, &maps.c, &bars[FULLC0 + s], 64, g, t0, b);
+          }
         }
         if (c >= 2) mbar_wait(&bars[EMPTYX0 + s], (u - 1) & 1);
         TV_TRACE(14, c);
         uint8_t* xs_ = smem + OFF_X + s * XSTAGE;
-        mbar_arrive_expect_tx(&bars[FULLX0 + s], XSTAGE);
+        mbar_arrive_expect_tx(&bars[FULLX0 + s], TV_ABLATE(8) ? 1024 : XSTAGE);
+        if (!TV_ABLATE(8))
 #pragma unroll
         for (int i = 0; i < 5; ++i) tma_load_4d(xs_ + i * 4096, &maps.x, &bars[FULLX0 + s], 16 * i, h, t0, b);
         bulk_load(xs_ + TILE_X, a.cs + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULLX0 + s]);
@@ -254,6 +267,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         TV_TRACE(1, c);
         const uint32_t so = (uint32_t)(s * (TILE_BC >> 4));
         const uint64_t dc = umma_desc_advance(dC_k, so), db = umma_desc_advance(dB_k, so);
+        if (!TV_ABLATE(4))
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
@@ -274,6 +288,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         TV_TRACE(2, c);
         {
           const uint64_t db = umma_desc_advance(dB_mn, so);
+          if (!TV_ABLATE(7))
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             umma_ss(tmem + T_ST, umma_desc_advance(db, j * 128), umma_desc_advance(dXS, j * 32), ID_ST, 1u);
@@ -289,6 +304,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           TV_TRACE(3, c);
           {
             const uint64_t dc = umma_desc_advance(dC_k, so);
+            if (!TV_ABLATE(5))
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
@@ -305,6 +321,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           {
             const uint64_t dx = umma_desc_advance(dX, (uint32_t)(s * (XSTAGE >> 4)));
             const uint32_t tmA = tmem + (s ? T_M1 : T_M0);
+            if (!TV_ABLATE(6))
 #pragma unroll
             for (int j = 0; j < 8; ++j) umma_ts(tmem + T_YD, tmA + j * 8, umma_desc_advance(dx, j * 32), ID_Y, j > 0);
           }
@@ -367,7 +384,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         const uint32_t tcb = tmem + T_CB + lane_base;
         const uint32_t tm = tmem + (s ? T_M1 : T_M0) + lane_base;
 #pragma unroll 1
-        for (int kb = kb_lo; kb < kb_hi; ++kb) {   // rolled on purpose: one copy of each block body in the I-cache
+        for (int kb = kb_lo; kb < (TV_ABLATE(1) ? kb_lo : kb_hi); ++kb) {   // rolled on purpose: one copy of each block body in the I-cache
           if (kb < q) m_block_offdiag(tcb + kb * 32, tm + kb * 16, sF + q * 128 + kb * 32, um);
           else m_block<DFOLD>(tcb + kb * 32, tm + kb * 16, sF + kb * 32, Em, lane, Dh, true);
         }
@@ -416,6 +433,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       // ---- state row n = r: decay in place (critical path) and bf16 copy of the un-decayed entering state.
       //      O(c-1) is issued right behind S(c-1), so the copy buffer is (almost always) already free here.
       if (FULL && c > 0) mbar_wait(&bars[YOFFDONE], (c - 1) & 1);
+      if (!TV_ABLATE(2))
 #pragma unroll
       for (int half = 0; half < 2; ++half) {       // 48 + 32 columns: two TMEM round trips instead of five
         const int c0 = half * 48, nc = half ? 2 : 3;
@@ -538,6 +556,11 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           }
           if (t < a.L) st_global_v8(orow + pc * 16, pk);
         };
+        if (TV_ABLATE(0)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[YEMPTY]);
+        } else
 #pragma unroll
         for (int pc = 0; pc < 5; pc += 2) {
           if (pc + 1 < 5) {
@@ -744,6 +767,8 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
 }
 
 // ------------------------------------------------------------------------------------------------ host
+static int g_ablate = 0;
+void set_ablate(int m) { g_ablate = m; }
 static void* g_trace_ptr = nullptr;   // debug: device buffer of nchunks*16 int64 (tv_debug_set_trace)
 void set_trace_buffer(void* p) { g_trace_ptr = p; }
 bool tc_supported(const tv_ssd_params& p) {
@@ -815,6 +840,7 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
   a.out = (__nv_bfloat16*)p.out; a.fin = p.final_states; a.logdecay = p.logdecay_sum;
   a.L = p.seqlen; a.H = p.nheads; a.G = p.ngroups; a.nchunks = nchunks; a.d_has_hdim = p.d_has_hdim;
   a.trace = (long long*)g_trace_ptr;
+  a.ablate = g_ablate;
   a.zbs = p.z_batch_stride; a.zss = p.z_seq_stride; a.zhs = p.z_head_stride;
   dim3 grid(p.nheads, p.batch);
   auto launch = [&](auto kern) -> int {

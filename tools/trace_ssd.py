@@ -7,9 +7,11 @@ from timeviper_b200 import _lib
 from tests.test_gpu_ops import _ssd_inputs
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+ABL = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 n = L // 128
 x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(1, L, 128, 80, 8, 128, torch.bfloat16, seed=1)
 run = lambda: tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, dt_bias=dt_bias, dt_softplus=True, return_final_states=True)
+_lib.load().tv_debug_set_ablate(ABL)
 run(); torch.cuda.synchronize()
 buf = torch.zeros(2 * n * 16, dtype=torch.int64, device="cuda")
 _lib.load().tv_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
