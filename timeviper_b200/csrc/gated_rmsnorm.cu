@@ -79,11 +79,27 @@ gated_rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ z, const T* 
         if (GATE_FIRST) {
           float zv[V];
           unpack16<T>(zr[GATE_FIRST ? i : 0], zv);
+          if (FAST) {   // packed f32x2 forms around the two MUFU per element (the kernel is issue-bound next to HBM)
 #pragma unroll
-          for (int j = 0; j < V; ++j) xv[j] *= silu<FAST>(zv[j]);
+            for (int j = 0; j < V; j += 2) {
+              const float2 z2 = make_float2(zv[j], zv[j + 1]);
+              const float2 tneg = __fmul2_rn(z2, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+              const float2 d = __fadd2_rn(make_float2(ex2_approx_f(tneg.x), ex2_approx_f(tneg.y)), make_float2(1.f, 1.f));
+              const float2 g2 = __fmul2_rn(z2, make_float2(rcp_approx_f(d.x), rcp_approx_f(d.y)));
+              const float2 u2 = __fmul2_rn(make_float2(xv[j], xv[j + 1]), g2);
+              xv[j] = u2.x; xv[j + 1] = u2.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) xv[j] *= silu<false>(zv[j]);
+          }
         }
+        {
+          float2 ss2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < V; ++j) ss = fmaf(xv[j], xv[j], ss);
+          for (int j = 0; j < V; j += 2) ss2 = __ffma2_rn(make_float2(xv[j], xv[j + 1]), make_float2(xv[j], xv[j + 1]), ss2);
+          ss += ss2.x + ss2.y;
+        }
         held[half * (NORM_MAXV / 2) + i].put(xv);
       }
     }
@@ -98,7 +114,10 @@ gated_rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ z, const T* 
       load16<T>(wp + vi * V, ww);
       held[i].get(o);
 #pragma unroll
-      for (int j = 0; j < V; ++j) o[j] = o[j] * rstd * ww[j];
+      for (int j = 0; j < V; j += 2) {
+        const float2 o2 = __fmul2_rn(__fmul2_rn(make_float2(o[j], o[j + 1]), make_float2(rstd, rstd)), make_float2(ww[j], ww[j + 1]));
+        o[j] = o2.x; o[j + 1] = o2.y;
+      }
       if (HAS_BIAS) {
         float bb[V];
         load16<T>(bias + (int64_t)g * group_size + vi * V, bb);
