@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TV_ABI_VERSION 1
+#define TV_ABI_VERSION 2
 
 typedef enum { TV_F32 = 0, TV_BF16 = 1 } tv_dtype;
 
@@ -92,8 +92,11 @@ int tv_gated_rmsnorm_fwd(const tv_rmsnorm_params* p, void* stream);
  * Head h reads group h / (H/G).  x/z/B/C have unit stride on their last dim; out is contiguous.
  * `mode`: TV_SSD_FULL computes out (+final_states); TV_SSD_STATE_ONLY computes only final_states and
  * chunk_logdecay_sum (the shard summary of the sequence-sharded path) and touches neither out, C, D nor z.
+ * TV_SSD_DT_ONLY runs only the dt activation + per-chunk cumsum into `workspace` (it reads dt, A, dt_bias and no
+ * other tensor -- x/B are only inspected for the family choice), so that a caller can overlap it with the conv
+ * that produces x/B/C and pass reuse_dt_cumsum = 1 to the calls that follow.
  * ------------------------------------------------------------------------------------------- */
-typedef enum { TV_SSD_FULL = 0, TV_SSD_STATE_ONLY = 1 } tv_ssd_mode;
+typedef enum { TV_SSD_FULL = 0, TV_SSD_STATE_ONLY = 1, TV_SSD_DT_ONLY = 2 } tv_ssd_mode;
 
 typedef struct {
   const void* x; const void* dt; const float* A; const void* B; const void* C;
@@ -130,12 +133,15 @@ int tv_ssd_kernel_family(const tv_ssd_params* p);
  * Sequence-sharded prefill: fold the gathered per-shard summaries into the state entering shard `rank`.
  *   S_in(0) = initial (or 0);  S_in(r+1) = exp(logdecay[r]) * S_in(r) + states[r]
  * states: (world, b, H, P, N) f32, logdecay: (world, b, H) f32 (as gathered), out: (b, H, P, N) f32.
+ * *_rank_stride: elements between consecutive ranks' summaries (0 = densely packed), so that one flat
+ * all-gather buffer [S_r | logdecay_r] per rank can be folded in place.
  * New work (the reference has no sequence parallelism); the hook it plugs into is
  * the `initial_states=` argument of mamba_chunk_scan_combined (my_ssd_combined.py:1280,1300).
  * ------------------------------------------------------------------------------------------- */
 int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, const float* initial,
                                 float* out, int32_t rank, int32_t batch, int32_t nheads,
-                                int32_t headdim, int32_t dstate, void* stream);
+                                int32_t headdim, int32_t dstate, int64_t states_rank_stride,
+                                int64_t logdecay_rank_stride, void* stream);
 
 /* Debug hook (profiling only): device buffer of nchunks*16 int64 that CTA (0,0) of the fused SSD kernel fills
  * with clock64() stamps of its pipeline events; NULL (default) disables it. */

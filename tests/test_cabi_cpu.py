@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert set(declared) == set(L.EXPORTS)
-    assert lib.tv_abi_version() == 1
+    assert lib.tv_abi_version() == L.TV_ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():

@@ -18,7 +18,7 @@ def _oracle_ops():
         out, _ = R.causal_conv1d_ref(x, weight, bias, initial_states, activation, dtype=torch.float64)
         return out
 
-    def summary(x, dt, A, B, chunk_size, dt_bias=None, dt_softplus=False, dt_limit=(0.0, float("inf"))):
+    def summary(x, dt, A, B, chunk_size, dt_bias=None, dt_softplus=False, dt_limit=(0.0, float("inf")), **kw):
         C0 = torch.zeros_like(B)
         _, s = R.ssd_chunked_ref(x, dt, A, B, C0, chunk_size, dt_bias=dt_bias, dt_softplus=dt_softplus,
                                  dt_limit=dt_limit, dtype=torch.float64)

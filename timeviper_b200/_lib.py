@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TV_LIB_PATH") or os.path.join(HERE, "libtimeviper_b200.so")   # TV_LIB_PATH: tuning builds
 
 TV_F32, TV_BF16 = 0, 1
-TV_SSD_FULL, TV_SSD_STATE_ONLY = 0, 1
+TV_SSD_FULL, TV_SSD_STATE_ONLY, TV_SSD_DT_ONLY = 0, 1, 2
+TV_ABI_VERSION = 2
 TV_OK, TV_ERR_INVALID, TV_ERR_UNSUPPORTED, TV_ERR_CUDA, TV_ERR_WORKSPACE = 0, -1, -2, -3, -4
 
 
@@ -58,7 +59,7 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m timeviper_b200.build` "
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python timeviper_b200/build.py` "
                           "(there is no CPU or PyTorch fallback for this path)")
     lib = C.CDLL(LIB_PATH)
     lib.tv_abi_version.restype = C.c_int
@@ -74,14 +75,15 @@ def load():
     lib.tv_ssd_kernel_family.argtypes = [C.POINTER(SsdParams)]
     lib.tv_ssd_kernel_family.restype = C.c_int
     lib.tv_ssd_fold_boundary_states.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+                                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                                C.c_void_p]
     lib.tv_ssd_fold_boundary_states.restype = C.c_int
     lib.tv_debug_set_trace.argtypes = [C.c_void_p]
     lib.tv_debug_set_trace.restype = None
     lib.tv_debug_set_ablate.argtypes = [C.c_int]
     lib.tv_debug_set_ablate.restype = None
-    if lib.tv_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.tv_abi_version()} != 1")
+    if lib.tv_abi_version() != TV_ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.tv_abi_version()} != {TV_ABI_VERSION} (rebuild the library)")
     _lib = lib
     return lib
 

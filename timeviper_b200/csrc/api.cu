@@ -19,7 +19,8 @@ void set_error(const char* fmt, ...) {
 static int validate_ssd(const tv_ssd_params* p) {
   TV_CHECK_ARG(p != nullptr, "ssd: null params");
   TV_CHECK_ARG(p->dtype == TV_F32 || p->dtype == TV_BF16, "ssd: dtype %d", p->dtype);
-  TV_CHECK_ARG(p->mode == TV_SSD_FULL || p->mode == TV_SSD_STATE_ONLY, "ssd: mode %d", p->mode);
+  TV_CHECK_ARG(p->mode == TV_SSD_FULL || p->mode == TV_SSD_STATE_ONLY || p->mode == TV_SSD_DT_ONLY, "ssd: mode %d",
+               p->mode);
   TV_CHECK_ARG(p->batch > 0 && p->seqlen > 0 && p->nheads > 0 && p->headdim > 0 && p->ngroups > 0 &&
                    p->dstate > 0 && p->chunk_size > 0,
                "ssd: empty problem (b=%d L=%d H=%d P=%d G=%d N=%d Q=%d)", p->batch, p->seqlen, p->nheads,
@@ -27,7 +28,8 @@ static int validate_ssd(const tv_ssd_params* p) {
   TV_CHECK_ARG(p->nheads % p->ngroups == 0, "ssd: nheads %d %% ngroups %d != 0", p->nheads, p->ngroups);
   TV_CHECK_ARG(p->x && p->dt && p->A && p->B, "ssd: x, dt, A, B must be non-null");
   if (p->mode == TV_SSD_FULL) TV_CHECK_ARG(p->C && p->out, "ssd: C and out must be non-null");
-  else TV_CHECK_ARG(p->final_states != nullptr, "ssd: state-only mode needs final_states");
+  else if (p->mode == TV_SSD_STATE_ONLY)
+    TV_CHECK_ARG(p->final_states != nullptr, "ssd: state-only mode needs final_states");
   return TV_OK;
 }
 
@@ -59,6 +61,7 @@ extern "C" int tv_ssd_chunk_scan_fwd(const tv_ssd_params* p, void* workspace, si
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (tv_ssd_kernel_family(p) == 1) return ssd_tc_forward(*p, workspace, s);
+  if (p->mode == TV_SSD_DT_ONLY) return TV_OK;   // the CUDA-core family recomputes dt/cumsum in every call
   rc = simt_supported(*p);
   if (rc != TV_OK) return rc;
   return ssd_simt_forward(*p, workspace, s);

@@ -7,14 +7,16 @@
 //
 // Roofline: pure HBM streaming, 2 * dim * sizeof(T) bytes per token (49,152 B at dim 12288, bf16).
 // Layout/tiling: one thread owns 16 bytes of channels (8 bf16 / 4 fp32) and walks TOK consecutive tokens with the
-// K-1 previous rows kept in registers, so every x element is read once per CTA (halo re-read = (K-1)/TOK, served
+// K-1 previous rows kept in registers, so every x element is read once per CTA (halo re-read = (K-1)/tok, served
 // from L2); a warp reads/writes 512 contiguous bytes per token row.
 #include "common.cuh"
 
 namespace tv {
 
 constexpr int CONV_THREADS = 128;
-constexpr int CONV_TOK = 64;   // tokens per CTA along the sequence
+// Tokens per CTA along the sequence (a template argument): longer runs amortise the weight / halo prologue (measured
+// at 128K tokens: 64 -> 77%, 128 -> 80%, 256 -> 81% of the HBM peak), shorter ones keep enough CTAs for short shards.
+constexpr int CONV_TOK_LONG = 128, CONV_TOK_SHORT = 64;
 // channels per thread = one 16-byte access: 8 (bf16) / 4 (fp32); a warp covers 512 contiguous bytes per token row
 constexpr int CONV_U = 8;      // independent row loads in flight per thread (kept as raw words until used)
 
@@ -27,7 +29,7 @@ template <typename T> struct Raw4 {   // register image of one 16-byte access
 
 // <= 128 registers per thread => 4 CTAs (16 warps) per SM, each thread keeping CONV_U raw row loads in flight:
 // 16 warps * 8 loads * 512 B = 64 KB in flight per SM, above the ~45 KB that 6.5 TB/s needs at ~1 us latency.
-template <typename T, int K, bool SILU>
+template <typename T, int K, bool SILU, int TOK>
 __global__ void __launch_bounds__(CONV_THREADS, 4)
 conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T* __restrict__ bias,
                   const T* __restrict__ init, T* __restrict__ out, T* __restrict__ fin,
@@ -37,8 +39,8 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
   const int c0 = (blockIdx.x * CONV_THREADS + threadIdx.x) * V;
   if (c0 >= dim) return;
   const int b = blockIdx.z;
-  const int t0 = blockIdx.y * CONV_TOK;
-  const int t1 = min(t0 + CONV_TOK, L);
+  const int t0 = blockIdx.y * TOK;
+  const int t1 = min(t0 + TOK, L);
   x += (int64_t)b * xbs + c0;
   out += (int64_t)b * obs + c0;
 
@@ -123,8 +125,13 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
 template <typename T, int K>
 static int launch_conv(const tv_conv1d_params& p, cudaStream_t s) {
   constexpr int V = Vec16<T>::N;
-  dim3 grid((unsigned)ceil_div(p.dim / V, CONV_THREADS), (unsigned)ceil_div(p.seqlen, CONV_TOK), p.batch);
-  auto kern = p.silu ? conv1d_fwd_kernel<T, K, true> : conv1d_fwd_kernel<T, K, false>;
+  // long runs only when they still leave >= 8 waves of CTAs (148 SMs x 4 resident)
+  const int64_t xblocks = ceil_div(p.dim / V, CONV_THREADS);
+  const int tok = xblocks * ceil_div(p.seqlen, CONV_TOK_LONG) * p.batch >= 8 * 148 * 4 ? CONV_TOK_LONG : CONV_TOK_SHORT;
+  dim3 grid((unsigned)xblocks, (unsigned)ceil_div(p.seqlen, tok), p.batch);
+  auto kern = tok == CONV_TOK_LONG
+                  ? (p.silu ? conv1d_fwd_kernel<T, K, true, CONV_TOK_LONG> : conv1d_fwd_kernel<T, K, false, CONV_TOK_LONG>)
+                  : (p.silu ? conv1d_fwd_kernel<T, K, true, CONV_TOK_SHORT> : conv1d_fwd_kernel<T, K, false, CONV_TOK_SHORT>);
   kern<<<grid, CONV_THREADS, 0, s>>>((const T*)p.x, (const T*)p.weight, (const T*)p.bias,
                                      (const T*)p.initial_states, (T*)p.out, (T*)p.final_states, p.dim,
                                      p.seqlen, p.x_batch_stride, p.x_seq_stride, p.out_batch_stride,

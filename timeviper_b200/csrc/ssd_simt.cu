@@ -420,29 +420,41 @@ int ssd_simt_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fold_boundary_kernel(const float* __restrict__ states, const float* __restrict__ logdecay,
-                     const float* __restrict__ init, float* __restrict__ out, int rank, int64_t BH, int PN) {
+                     const float* __restrict__ init, float* __restrict__ out, int rank, int64_t srs, int64_t lrs,
+                     int PN4) {
+  // one thread = 4 consecutive state elements (PN % 4 == 0); the decay chain is re-evaluated per thread (rank <= 7)
   const int64_t bh = blockIdx.y;
   const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e >= PN) return;
-  float s = init != nullptr ? init[bh * PN + e] : 0.f;
-  for (int r = 0; r < rank; ++r)
-    s = fmaf(expf(logdecay[(int64_t)r * BH + bh]), s, states[((int64_t)r * BH + bh) * PN + e]);
-  out[bh * PN + e] = s;
+  if (e >= PN4) return;
+  const int64_t off = bh * PN4 + e;
+  float4 s = init != nullptr ? reinterpret_cast<const float4*>(init)[off] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < rank; ++r) {
+    const float d = expf(logdecay[(int64_t)r * lrs + bh]);
+    const float4 v = *reinterpret_cast<const float4*>(states + (int64_t)r * srs + off * 4);
+    s.x = fmaf(d, s.x, v.x); s.y = fmaf(d, s.y, v.y); s.z = fmaf(d, s.z, v.z); s.w = fmaf(d, s.w, v.w);
+  }
+  reinterpret_cast<float4*>(out)[off] = s;
 }
 
 }  // namespace tv
 
 extern "C" int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, const float* initial,
                                            float* out, int32_t rank, int32_t batch, int32_t nheads,
-                                           int32_t headdim, int32_t dstate, void* stream) {
+                                           int32_t headdim, int32_t dstate, int64_t states_rank_stride,
+                                           int64_t logdecay_rank_stride, void* stream) {
   using namespace tv;
   TV_CHECK_ARG(out != nullptr && rank >= 0 && batch > 0 && nheads > 0 && headdim > 0 && dstate > 0,
                "fold_boundary_states: bad arguments");
   TV_CHECK_ARG(rank == 0 || (states != nullptr && logdecay != nullptr), "fold_boundary_states: null summaries");
-  const int PN = headdim * dstate;
-  dim3 grid((unsigned)ceil_div(PN, 256), (unsigned)(batch * nheads));
-  fold_boundary_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(states, logdecay, initial, out, rank,
-                                                              (int64_t)batch * nheads, PN);
+  const int64_t PN = (int64_t)headdim * dstate, BH = (int64_t)batch * nheads;
+  const int64_t srs = states_rank_stride > 0 ? states_rank_stride : BH * PN;
+  const int64_t lrs = logdecay_rank_stride > 0 ? logdecay_rank_stride : BH;
+  TV_CHECK_ARG(PN % 4 == 0 && srs % 4 == 0 && ((uintptr_t)states % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                   (initial == nullptr || (uintptr_t)initial % 16 == 0),
+               "fold_boundary_states: headdim*dstate and the rank stride must be multiples of 4, pointers 16-byte aligned");
+  dim3 grid((unsigned)ceil_div(PN / 4, 256), (unsigned)BH);
+  fold_boundary_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(states, logdecay, initial, out, rank, srs, lrs,
+                                                              (int)(PN / 4));
   TV_CUDA_OK(cudaGetLastError());
   return TV_OK;
 }

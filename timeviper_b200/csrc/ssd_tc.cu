@@ -801,6 +801,7 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
     int rc = launch_dt_cumsum(p, dt_act, cs, s);
     if (rc != TV_OK) return rc;
   }
+  if (p.mode == TV_SSD_DT_ONLY) return TV_OK;
 
   Maps maps;
   const uint64_t L = (uint64_t)p.seqlen;

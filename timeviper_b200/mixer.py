@@ -74,6 +74,26 @@ class Mamba2MixerPrefill(nn.Module):
         nn.init.kaiming_uniform_(self.out_proj.weight, a=math.sqrt(5))
         self.out_proj.weight /= math.sqrt(c.num_hidden_layers)
 
+    def decay_rates(self):
+        """A = -exp(A_log) in fp32 (modeling_nano.py:550-552), recomputed only when A_log changes."""
+        key = (self.A_log._version, self.A_log.data_ptr())
+        if getattr(self, "_A_key", None) != key:
+            self._A_val, self._A_key = -torch.exp(self.A_log.detach().float()), key
+        return self._A_val
+
+    def f32_param(self, name):
+        """fp32 image of a small per-head parameter (D, dt_bias), as the SSD kernels read them; cached until the
+        parameter changes, so a prefill step does not re-launch the conversion kernels."""
+        p = getattr(self, name)
+        if p.dtype == torch.float32:
+            return p.detach()
+        cache = self.__dict__.setdefault("_f32_cache", {})
+        key = (p._version, p.data_ptr())
+        hit = cache.get(name)
+        if hit is None or hit[0] != key:
+            hit = cache[name] = (key, p.detach().float())
+        return hit[1]
+
     # -- the three-kernel core, on an already projected input (what bench.py's `value` times) ------------
     def scan_core(self, projected_states, cache_params=None, conv_initial_states=None, ssm_initial_states=None,
                   return_states=False, return_conv_state=False):
@@ -95,12 +115,12 @@ class Mamba2MixerPrefill(nn.Module):
             conv_out, conv_final = conv_out
         hidden_states_B_C = conv_out.transpose(1, 2)
         hidden_states, B, C = torch.split(hidden_states_B_C, [self.intermediate_size, gts, gts], dim=-1)
-        A = -torch.exp(self.A_log.float())                                      # :550-552
+        A = self.decay_rates()                                                  # :550-552
         scan_output, ssm_state = ops.mamba_chunk_scan_combined(                 # :639-653
             hidden_states.view(batch_size, seq_len, -1, self.head_dim), dt, A,
             B.view(batch_size, seq_len, self.n_groups, -1), C.view(batch_size, seq_len, self.n_groups, -1),
-            chunk_size=self.chunk_size, D=self.D, z=None, seq_idx=None, return_final_states=True,
-            dt_bias=self.dt_bias, dt_softplus=True, dt_limit=self.time_step_limit,
+            chunk_size=self.chunk_size, D=self.f32_param("D"), z=None, seq_idx=None, return_final_states=True,
+            dt_bias=self.f32_param("dt_bias"), dt_softplus=True, dt_limit=self.time_step_limit,
             initial_states=ssm_initial_states)
         if ssm_state is not None and cache_params is not None:                  # :656-659
             cache_params.update_ssm_state(layer_idx=self.layer_idx, new_ssm_state=ssm_state)

@@ -48,6 +48,13 @@ def causal_conv1d_fn(x, weight, bias=None, seq_idx=None, initial_states=None, re
     weight: (dim, width); bias: (dim,); initial_states: (batch, dim, width-1);
     activation: None | "silu" | "swish".  Returns out (batch, dim, seqlen) channel-last
     [, final_states (batch, dim, width-1)]."""
+    return causal_conv1d_into(None, x, weight, bias, seq_idx, initial_states, return_final_states,
+                              final_states_out, activation)
+
+
+def causal_conv1d_into(_out, x, weight, bias=None, seq_idx=None, initial_states=None, return_final_states=False,
+                       final_states_out=None, activation=None):
+    """causal_conv1d_fn writing into `_out`, a caller-owned (batch, seqlen, dim) buffer (None: allocate)."""
     if activation not in (None, "silu", "swish"):
         raise NotImplementedError("activation must be None, silu, or swish")
     if seq_idx is not None:
@@ -67,7 +74,12 @@ def causal_conv1d_fn(x, weight, bias=None, seq_idx=None, initial_states=None, re
         if tuple(initial_states.shape) != (b, dim, width - 1):
             raise ValueError("causal_conv1d_fn: initial_states must be (batch, dim, width-1)")
         initial_states = initial_states.to(x.dtype).contiguous()
-    out = torch.empty((b, seqlen, dim), dtype=x.dtype, device=x.device)
+    if _out is not None:
+        if tuple(_out.shape) != (b, seqlen, dim) or _out.dtype != x.dtype or _out.stride(2) != 1:
+            raise ValueError("causal_conv1d_fn: _out must be (batch, seqlen, dim) of x's dtype, unit channel stride")
+        out = _out
+    else:
+        out = torch.empty((b, seqlen, dim), dtype=x.dtype, device=x.device)
     fin = None
     if return_final_states or final_states_out is not None:
         if final_states_out is not None:
@@ -124,9 +136,11 @@ def rmsnorm_fn(x, weight, bias, z=None, eps=1e-6, group_size=None, norm_before_g
 _workspaces = {}
 
 
-def _workspace(nbytes, device):
-    """Grow-only scratch per (device, stream): the .so never allocates (ownership)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+def _workspace(nbytes, device, owner_stream=None):
+    """Grow-only scratch per (device, stream): the .so never allocates (ownership).
+    `owner_stream`: the stream whose scratch to use when a call is enqueued on a helper stream."""
+    owner = owner_stream if owner_stream is not None else torch.cuda.current_stream(device)
+    key = (device.index, owner.cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
@@ -135,7 +149,8 @@ def _workspace(nbytes, device):
 
 
 def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_softplus, dt_limit, mode,
-              force_simt=False, want_final=True, want_logdecay=False, reuse_dt_cumsum=False):
+              force_simt=False, want_final=True, want_logdecay=False, reuse_dt_cumsum=False, final_out=None,
+              logdecay_out=None, workspace_stream=None):
     batch, seqlen, nheads, headdim = x.shape
     ngroups, dstate = B.shape[2], B.shape[3]
     assert nheads % ngroups == 0
@@ -176,8 +191,15 @@ def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_sof
     out = None
     if mode == L.TV_SSD_FULL:
         out = torch.empty((batch, seqlen, nheads, headdim), dtype=x.dtype, device=dev)
-    fin = torch.empty((batch, nheads, headdim, dstate), dtype=torch.float32, device=dev) if want_final else None
-    logdecay = torch.empty((batch, nheads), dtype=torch.float32, device=dev) if want_logdecay else None
+    fin = logdecay = None
+    if want_final:
+        fin = final_out if final_out is not None else torch.empty((batch, nheads, headdim, dstate),
+                                                                  dtype=torch.float32, device=dev)
+        assert fin.shape == (batch, nheads, headdim, dstate) and fin.dtype == torch.float32 and fin.is_contiguous()
+    if want_logdecay:
+        logdecay = logdecay_out if logdecay_out is not None else torch.empty((batch, nheads), dtype=torch.float32,
+                                                                             device=dev)
+        assert logdecay.shape == (batch, nheads) and logdecay.dtype == torch.float32 and logdecay.is_contiguous()
     p = L.SsdParams(
         x=_ptr(x), dt=_ptr(dt), A=_ptr(A32), B=_ptr(B), C=_ptr(C_), D=_ptr(D32), z=_ptr(z),
         dt_bias=_ptr(bias32), initial_states=_ptr(init32), out=_ptr(out), final_states=_ptr(fin),
@@ -195,7 +217,7 @@ def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_sof
         force_simt=int(bool(force_simt)), reuse_dt_cumsum=int(bool(reuse_dt_cumsum)))
     lib = L.load()
     need = lib.tv_ssd_workspace_bytes(C.byref(p))
-    ws = _workspace(need, dev)
+    ws = _workspace(need, dev, workspace_stream)
     L.check(lib.tv_ssd_chunk_scan_fwd(C.byref(p), _ptr(ws), ws.numel(), _stream(x)), "mamba_chunk_scan_combined")
     return out, fin, logdecay
 
@@ -222,25 +244,49 @@ def mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bia
 
 
 def mamba_chunk_state_summary(x, dt, A, B, chunk_size, dt_bias=None, dt_softplus=False,
-                              dt_limit=(0.0, float("inf")), _force_simt=False):
+                              dt_limit=(0.0, float("inf")), _force_simt=False, _reuse_dt_cumsum=False, out=None):
     """Shard summary for the sequence-sharded path: (final state from a zero initial state (b,H,P,N) fp32,
-    sum over the shard of dt*A (b,H) fp32).  New work -- SURVEY.md section 8e."""
+    sum over the shard of dt*A (b,H) fp32).  `out` = (states, logdecay) buffers to fill (e.g. views of one
+    flat all-gather send buffer).  New work -- SURVEY.md section 8e."""
     _, fin, logdecay = _ssd_call(x, dt, A, B, None, chunk_size, None, None, dt_bias, None, dt_softplus,
                                  dt_limit, L.TV_SSD_STATE_ONLY, force_simt=_force_simt, want_final=True,
-                                 want_logdecay=True)
+                                 want_logdecay=True, reuse_dt_cumsum=_reuse_dt_cumsum,
+                                 final_out=None if out is None else out[0],
+                                 logdecay_out=None if out is None else out[1])
     return fin, logdecay
 
 
+def mamba_dt_cumsum_prepare(x, dt, A, B, chunk_size, dt_bias=None, dt_softplus=False,
+                            dt_limit=(0.0, float("inf")), workspace_stream=None):
+    """Runs only the dt activation + per-chunk cumsum into the scratch owned by `workspace_stream` (default: the
+    current stream), so that it can overlap the conv that produces x/B; x and B are NOT read (only their
+    pointers/strides are inspected).  Follow with `_reuse_dt_cumsum=True` calls on the owning stream."""
+    _ssd_call(x, dt, A, B, None, chunk_size, None, None, dt_bias, None, dt_softplus, dt_limit, L.TV_SSD_DT_ONLY,
+              want_final=False, workspace_stream=workspace_stream)
+
+
+def _rank_strided(t):
+    """True if t (world, ...) is dense within each rank (only the rank stride may be padded)."""
+    return t[0].is_contiguous() if t.shape[0] > 0 else True
+
+
 def fold_boundary_states(states, logdecay, rank, initial_states=None):
-    """states (world,b,H,P,N) fp32, logdecay (world,b,H) fp32 -> state entering shard `rank` (b,H,P,N)."""
+    """states (world,b,H,P,N) fp32, logdecay (world,b,H) fp32 -> state entering shard `rank` (b,H,P,N).
+    Both may be views of one flat gathered buffer (any rank stride)."""
     _require_cuda(states, logdecay, initial_states)
     world, b, H, P, N = states.shape
-    states = states.to(torch.float32).contiguous()
-    logdecay = logdecay.to(torch.float32).contiguous()
+    states = states.to(torch.float32)
+    logdecay = logdecay.to(torch.float32)
+    if not _rank_strided(states) or states.stride(0) % 4 or states.data_ptr() % 16:
+        states = states.contiguous()
+    if not _rank_strided(logdecay):
+        logdecay = logdecay.contiguous()
     init = None if initial_states is None else initial_states.to(torch.float32).contiguous()
     out = torch.empty((b, H, P, N), dtype=torch.float32, device=states.device)
     L.check(L.load().tv_ssd_fold_boundary_states(_ptr(states), _ptr(logdecay), _ptr(init), _ptr(out), int(rank),
-                                                 b, H, P, N, _stream(states)), "fold_boundary_states")
+                                                 b, H, P, N, states.stride(0) if world > 1 else 0,
+                                                 logdecay.stride(0) if world > 1 else 0, _stream(states)),
+            "fold_boundary_states")
     return out
 
 

@@ -3,28 +3,48 @@
 New work: the reference has no sequence/context parallelism (SURVEY.md sections 5, 8e).  Rank r holds the
 contiguous shard r of the sequence (all heads, replicated parameters).  Per layer:
 
-  1. local: in_proj; exchange the K-1 = 3 pre-conv rows that precede the shard (conv halo) with an
-     all-gather; conv with ``initial_states`` = halo of rank r-1.
-  2. local pass 1: shard summary (S_r = state after the shard from a zero state, log P_r = sum dt*A).
-  3. ONE collective: all-gather of (S_r, log P_r)  -- 5.24 MB + 512 B per rank at the 9B dims,
+  1. local: in_proj.  The K-1 = 3 pre-conv rows that precede the shard (conv halo) are all-gathered on a HELPER
+     stream while the main stream already runs the conv over the whole shard with a zero halo; the helper stream
+     also runs the dt softplus/cumsum (it needs only dt) and, once the halo is there, re-does the conv of the first
+     K-1 rows (the only ones that see the halo).  Join; patch the K-1 rows.
+  2. local pass 1: shard summary (S_r = state after the shard from a zero state, log P_r = sum dt*A), written
+     straight into one flat send buffer [S_r | log P_r].
+  3. ONE collective on the critical path: all-gather of that buffer -- 5.24 MB + 512 B per rank at the 9B dims,
      independent of L -- over NCCL/NVLink.
-  4. local: fold ranks < r in fp32:  S_in(r+1) = exp(log P_r) S_in(r) + S_r.
-  5. local pass 2: the full scan with ``initial_states = S_in(r)``; gated norm; out_proj.
+  4. local: fold ranks < r in fp32:  S_in(r+1) = exp(log P_r) S_in(r) + S_r   (reads the gathered buffer in place).
+  5. local pass 2: the full scan with ``initial_states = S_in(r)`` (dt/cumsum reused); gated norm; out_proj.
 
 The final SSM state of the sequence is rank W-1's; the final conv state is rank W-1's last K rows.
-``ops`` is injectable so that the host-side logic (halo, gather, fold order) is testable with gloo on CPU.
+``ops`` is injectable so that the host-side logic (halo patch, gather, fold order) is testable with gloo on CPU.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 from torch import nn
 
 from . import ops as _cuda_ops
 
+_helper_streams = {}
 
-def _all_gather_cat(t, group):
+
+def _helper_stream(device):
+    """High-priority side stream: its small kernels (dt cumsum, halo conv) are scheduled into the SM slots that the
+    shard-wide conv on the main stream frees, instead of queueing behind its whole grid."""
+    s = _helper_streams.get(device.index)
+    if s is None:
+        s = _helper_streams[device.index] = torch.cuda.Stream(device, priority=-1)
+    return s
+
+
+def _all_gather_rows(send, group):
+    """send: contiguous tensor -> (world, *send.shape), one collective, no staging copy."""
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    dist.all_gather(list(out.unbind(0)), t.contiguous(), group=group)   # views of `out`: no extra copy
+    out = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+    if send.is_cuda:
+        dist.all_gather_into_tensor(out.view(-1), send.view(-1), group=group)
+    else:                       # gloo: list form, the outputs are views of `out`
+        dist.all_gather(list(out.unbind(0)), send, group=group)
     return out
 
 
@@ -33,37 +53,73 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     b, L, _ = projected_states.shape
     K = mixer.conv_kernel_size
-    gts = mixer.n_groups * mixer.ssm_state_size
-    gate, xBC, dt = projected_states.split([mixer.intermediate_size, mixer.conv_dim, mixer.num_heads], dim=-1)
-
-    # 1. conv halo: last K-1 pre-conv rows of every shard (b, K-1, conv_dim)
+    H, P, G, N = mixer.num_heads, mixer.head_dim, mixer.n_groups, mixer.ssm_state_size
+    gate, xBC, dt = projected_states.split([mixer.intermediate_size, mixer.conv_dim, H], dim=-1)
     assert L >= K - 1, "a shard must hold at least conv_kernel-1 tokens"
-    halos = _all_gather_cat(xBC[:, L - (K - 1):, :], group)
-    conv_init = None if rank == 0 else halos[rank - 1].transpose(1, 2).contiguous()   # (b, conv_dim, K-1)
-    xBC_c = ops.causal_conv1d_fn(x=xBC.transpose(1, 2), weight=mixer.conv1d.weight.squeeze(1),
-                                 bias=mixer.conv1d.bias, initial_states=conv_init,
-                                 activation=mixer.activation).transpose(1, 2)
-    x, B, C = torch.split(xBC_c, [mixer.intermediate_size, gts, gts], dim=-1)
-    x = x.view(b, L, -1, mixer.head_dim)
-    B = B.view(b, L, mixer.n_groups, -1)
-    C = C.view(b, L, mixer.n_groups, -1)
-    A = -torch.exp(mixer.A_log.float())
+    native = ops is _cuda_ops
+    dev = projected_states.device
+    A = mixer.decay_rates().to(dev)
+    w, bias = mixer.conv1d.weight.squeeze(1), mixer.conv1d.bias
+    scan_kw = dict(dt_bias=mixer.f32_param("dt_bias"), dt_softplus=True, dt_limit=mixer.time_step_limit)
 
-    # 2.-4. shard summary, one all-gather, local fold
-    S_r, logP_r = ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, dt_bias=mixer.dt_bias,
-                                                dt_softplus=True, dt_limit=mixer.time_step_limit)
-    packed = torch.cat([S_r.reshape(b, mixer.num_heads, -1), logP_r[..., None]], dim=-1)   # (b,H,P*N+1)
-    gathered = _all_gather_cat(packed, group)
-    S_all = gathered[..., :-1].reshape(world, b, mixer.num_heads, mixer.head_dim, mixer.ssm_state_size)
-    logP_all = gathered[..., -1]
+    # 1. conv over the shard (zero halo) || halo all-gather, dt cumsum, conv of the first K-1 rows with the halo
+    halo_send = xBC[:, L - (K - 1):, :].contiguous()                  # (b, K-1, conv_dim)
+    if native:
+        main, side = torch.cuda.current_stream(dev), _helper_stream(dev)
+        xBC_c = torch.empty((b, L, mixer.conv_dim), dtype=xBC.dtype, device=dev)
+        side.wait_stream(main)
+        side_ctx = torch.cuda.stream(side)
+        # the big kernel is enqueued first; the helper stream's small ones overtake it on the device (priority)
+        ops.causal_conv1d_into(xBC_c, x=xBC.transpose(1, 2), weight=w, bias=bias, activation=mixer.activation)
+    else:
+        xBC_c, side_ctx = None, contextlib.nullcontext()
+
+    def views(t):
+        x, B, C = torch.split(t, [mixer.intermediate_size, G * N, G * N], dim=-1)
+        return x.view(b, L, H, P), B.view(b, L, G, N), C.view(b, L, G, N)
+
+    head_rows = None
+    with side_ctx:
+        halos = _all_gather_rows(halo_send, group)                    # (world, b, K-1, conv_dim)
+        if native:                                                    # needs dt only; scratch of the main stream
+            x, B, C = views(xBC_c)
+            ops.mamba_dt_cumsum_prepare(x, dt, A, B, mixer.chunk_size, workspace_stream=main, **scan_kw)
+        if rank > 0:
+            conv_init = halos[rank - 1].transpose(1, 2).contiguous()  # (b, conv_dim, K-1)
+            head_rows = ops.causal_conv1d_fn(x=xBC[:, :K - 1].transpose(1, 2), weight=w, bias=bias,
+                                             initial_states=conv_init, activation=mixer.activation)
+    if native:
+        main.wait_stream(side)
+        for t in (halos, head_rows):
+            if t is not None:
+                t.record_stream(main)
+    else:
+        xBC_c = ops.causal_conv1d_fn(x=xBC.transpose(1, 2), weight=w, bias=bias,
+                                     activation=mixer.activation).transpose(1, 2).contiguous()
+    if head_rows is not None:
+        xBC_c[:, :K - 1].copy_(head_rows.transpose(1, 2))
+    x, B, C = views(xBC_c)
+
+    # 2.-4. shard summary into one flat buffer, one all-gather, fold in place
+    n = b * H * P * N
+    flat = torch.empty(n + b * H, dtype=torch.float32 if native else xBC_c.dtype, device=dev)
+    S_r, logP_r = flat[:n].view(b, H, P, N), flat[n:].view(b, H)
+    if native:
+        ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, _reuse_dt_cumsum=True, out=(S_r, logP_r),
+                                      **scan_kw)
+    else:
+        s, lp = ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, **scan_kw)
+        S_r.copy_(s)
+        logP_r.copy_(lp)
+    gathered = _all_gather_rows(flat, group)                          # (world, n + b*H)
+    S_all = gathered[:, :n].view(world, b, H, P, N)
+    logP_all = gathered[:, n:].view(world, b, H)
     S_in = ops.fold_boundary_states(S_all, logP_all, rank) if rank > 0 else None
 
-    # 5. full local scan from the folded entering state (dt/cumsum of pass 1 is still in the op's workspace)
-    reuse = {"_reuse_dt_cumsum": True} if ops is _cuda_ops else {}
-    y, ssm_state = ops.mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size=mixer.chunk_size, D=mixer.D, z=None,
-                                                 dt_bias=mixer.dt_bias, dt_softplus=True,
-                                                 dt_limit=mixer.time_step_limit, initial_states=S_in,
-                                                 return_final_states=True, **reuse)
+    # 5. full local scan from the folded entering state (dt/cumsum of step 1 is still in the op's scratch)
+    reuse = {"_reuse_dt_cumsum": True} if native else {}
+    y, ssm_state = ops.mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size=mixer.chunk_size, D=mixer.f32_param("D"), z=None,
+                                                 initial_states=S_in, return_final_states=True, **scan_kw, **reuse)
     if cache_params is not None and rank == world - 1:
         xt = xBC.transpose(1, 2)
         conv_states = nn.functional.pad(xt, (cache_params.conv_kernel_size - xt.shape[-1], 0))
