@@ -285,7 +285,10 @@ def run_ours(args):
             cpu_block = {"value": cpu_tps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.cpu_sample} tokens of the same layer, oracle/mamba2_ref.py (restatement of "
                                    f"the reference torch_forward), fp32, {cores} torch threads, {cpu_sec:.1f} s"}
-        launches_per_step = {"simt": 7, "tcgen05": 4}[family] + (3 if dist_on else 0)
+        # kernels of libtimeviper_b200.so per step on rank 0.  single GPU: conv, dt cumsum, fused SSD (5 stage kernels
+        # in the CUDA-core family), norm.  sharded: + suffix scan and state pass of pass 1 (the cumsum is shared by both
+        # passes); ranks > 0 add the 3-row halo conv and the boundary-state fold.
+        launches_per_step = {"simt": 7, "tcgen05": 4}[family] + (2 if dist_on else 0)
         line = {
             "metric": METRIC, "value": Ltot / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
