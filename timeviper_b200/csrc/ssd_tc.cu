@@ -18,7 +18,7 @@
 // Decay, mask and cumsum stay in fp32 registers; only the four contractions touch the tensor cores.
 //
 // Warp roles (576 threads): warps 0-3 = WG_A and 4-7 = WG_H (build M), warps 8-11 = WG_B (x scaling, state decay,
-// bf16 state copy), warps 12-15 = WG_C (epilogue), warp 16 = TMA producer (+ L2 prefetch 3 chunks ahead), warp 17 =
+// bf16 state copy), warps 12-15 = WG_C (epilogue), warp 16 = TMA producer, warp 17 =
 // MMA issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers so each is released as soon as
 // its last MMA has been issued.  Tensor-pipe order per iteration is S(c), O(c), D(c), G(c+1).
 #include "common.cuh"
@@ -31,6 +31,12 @@ using namespace sm100;
 
 namespace tc {
 constexpr int Q = 128, P = 80, N = 128;
+// L2 prefetch ahead of the smem loads, bitmask: 1 = x tiles, 2 = cs/dt rows, 4 = B/C tiles (group leader).  It paid
+// off in the first versions of the kernel; measured on the current one at 128K tokens it COSTS 1-5 % in every
+// combination (2.08 ms without, 2.18 / 2.10 / 2.09 / 2.16 / 2.20 ms with 1 / 2 / 4 / 6 / 7), so it is off.
+#ifndef TV_SSD_L2_PREFETCH
+#define TV_SSD_L2_PREFETCH 0
+#endif
 constexpr int THREADS = 576;                      // WG_A, WG_H, WG_B, WG_C (4 warps each) + producer + MMA issuer
 constexpr int W_A = 0, W_H = 4, W_B = 8, W_C = 12, W_PROD = 16, W_MMA = 17;   // first warp of each role
 constexpr uint32_t TILE_BC = Q * N * 2;          // 32768: two 16 KB halves (n 0..63 | 64..127), SW128
@@ -194,21 +200,25 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       const bool group_leader = (h % hpg) == 0;      // one CTA per group warms L2 with the shared B / C tiles
       auto l2_prefetch = [&](int c) {
         const int t0 = c * Q;
+        if (TV_SSD_L2_PREFETCH & 1) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) tma_prefetch_4d(&maps.x, 16 * i, h, t0, b);
-        bulk_prefetch(a.cs + (row0 + (int64_t)c * a.H) * Q, 512);
-        bulk_prefetch(a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512);
-        if (group_leader) {
+          for (int i = 0; i < 5; ++i) tma_prefetch_4d(&maps.x, 16 * i, h, t0, b);
+        }
+        if (TV_SSD_L2_PREFETCH & 2) {
+          bulk_prefetch(a.cs + (row0 + (int64_t)c * a.H) * Q, 512);
+          bulk_prefetch(a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512);
+        }
+        if ((TV_SSD_L2_PREFETCH & 4) && group_leader) {
           tma_prefetch_4d(&maps.b, 0, g, t0, b); tma_prefetch_4d(&maps.b, 64, g, t0, b);
           if (FULL) { tma_prefetch_4d(&maps.c, 0, g, t0, b); tma_prefetch_4d(&maps.c, 64, g, t0, b); }
         }
       };
       constexpr int PF = 3;                         // L2 prefetch distance (chunks ahead of the smem loads)
-      for (int c = 1; c < PF && c < n; ++c) l2_prefetch(c);
+      if (TV_SSD_L2_PREFETCH) for (int c = 1; c < PF && c < n; ++c) l2_prefetch(c);
       for (int c = 0; c < n; ++c) {
         const int s = c & 1, u = c >> 1;
         const int t0 = c * Q;
-        if (c + PF < n && !TV_ABLATE(10)) l2_prefetch(c + PF);
+        if (TV_SSD_L2_PREFETCH && c + PF < n && !TV_ABLATE(10)) l2_prefetch(c + PF);
         if (c >= 2) mbar_wait(&bars[EMPTYB0 + s], (u - 1) & 1);
         TV_TRACE(0, c);
 #ifdef TV_ENABLE_TRACE
@@ -554,7 +564,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
             if (HAS_Z) { y0 *= zv[2 * j]; y1 *= zv[2 * j + 1]; }
             pk[j] = pack_bf16x2(y0, y1);
           }
-          if (t < a.L) st_global_v8(orow + pc * 16, pk);
+          if (t < a.L && !TV_ABLATE(11)) st_global_v8(orow + pc * 16, pk);
         };
         if (TV_ABLATE(0)) {
           tc_fence_before();
