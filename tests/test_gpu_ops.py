@@ -184,6 +184,57 @@ def test_state_summary_and_fold(tv):
     assert relerr(fin, fin_full) < 1e-4
 
 
+def test_sharded_path_building_blocks_on_one_gpu(tv):
+    """The pieces `sharded.py` adds around the reference ops, checked without a second GPU (the round-end GPU tier
+    may have one device): dt/cumsum prepared on a helper stream into the main stream's scratch and reused; summaries
+    written into one flat [S | logP] buffer; the fold reading a rank-strided gathered buffer in place; conv into a
+    caller-owned buffer; the 3-row halo patch."""
+    from timeviper_b200 import ops
+    b, L, H, P, G, N, Q, W = 1, 1024, 8, 80, 2, 128, 128, 4
+    x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(b, L, H, P, G, N, torch.bfloat16, seed=9)
+    A = A * 0.01
+    kw = dict(dt_bias=dt_bias, dt_softplus=True)
+    ref, ref_fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, Q, D=D, return_final_states=True, **kw)
+    # dt-only on a side stream, then both passes with reuse
+    main, side = torch.cuda.current_stream(), torch.cuda.Stream(priority=-1)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        ops.mamba_dt_cumsum_prepare(x, dt, A, B, Q, workspace_stream=main, **kw)
+    main.wait_stream(side)
+    n = b * H * P * N
+    flat = torch.empty(n + b * H, dtype=torch.float32, device="cuda")
+    S, lp = ops.mamba_chunk_state_summary(x, dt, A, B, Q, _reuse_dt_cumsum=True,
+                                          out=(flat[:n].view(b, H, P, N), flat[n:].view(b, H)), **kw)
+    assert S.data_ptr() == flat.data_ptr()
+    out, fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, Q, D=D, return_final_states=True, _reuse_dt_cumsum=True, **kw)
+    assert torch.equal(out, ref) and torch.equal(fin, ref_fin)
+    assert relerr(S, ref_fin) < 2e-2
+    # fold over a gathered buffer with a padded rank stride == fold over dense copies
+    gathered = torch.randn(W, n + b * H, device="cuda")
+    gathered[:, n:] = -torch.rand(W, b * H, device="cuda")
+    S_all, lp_all = gathered[:, :n].view(W, b, H, P, N), gathered[:, n:].view(W, b, H)
+    for r in range(W):
+        a_ = tv.fold_boundary_states(S_all, lp_all, r)
+        b_ = tv.fold_boundary_states(S_all.contiguous(), lp_all.contiguous(), r)
+        assert torch.equal(a_, b_)
+        ref_fold = R.fold_boundary_states(list(S_all.cpu()), list(lp_all.cpu()), r, None)
+        if r:
+            assert relerr(a_, ref_fold) < 1e-5
+    # conv into a caller-owned buffer, and the halo patch of the first K-1 rows
+    dim, K = 256, 4
+    xx = torch.randn(1, 200, dim, device="cuda").to(torch.bfloat16)
+    w = torch.randn(dim, K, device="cuda").to(torch.bfloat16)
+    bias = torch.randn(dim, device="cuda").to(torch.bfloat16)
+    whole = tv.causal_conv1d_fn(xx.transpose(1, 2), w, bias, activation="silu")
+    buf = torch.empty(1, 100, dim, device="cuda", dtype=torch.bfloat16)
+    ops.causal_conv1d_into(buf, xx[:, 100:].transpose(1, 2), w, bias, activation="silu")          # zero halo
+    head = tv.causal_conv1d_fn(xx[:, 100:100 + K - 1].transpose(1, 2), w, bias,
+                               initial_states=xx[:, 100 - (K - 1):100].transpose(1, 2).contiguous(), activation="silu")
+    assert torch.equal(buf[:, K - 1:], whole.transpose(1, 2)[:, 100 + K - 1:])
+    buf[:, :K - 1].copy_(head.transpose(1, 2))
+    assert torch.equal(buf, whole.transpose(1, 2)[:, 100:])
+
+
 # ------------------------------------------------------------------------------------------------ mixer
 def _golden():
     return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mixer_*.npz")))

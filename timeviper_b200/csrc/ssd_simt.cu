@@ -67,6 +67,62 @@ ssd_dt_cumsum_kernel(const T* __restrict__ dt, const float* __restrict__ A, cons
   }
 }
 
+// bf16 fast path of (i) for unit head stride: a warp reads 64 heads of one token as ONE 128-byte request (two heads
+// per lane), the activated dt goes through shared memory as two [Q][33] planes (even / odd heads, conflict-free both
+// ways), and every head's chunk is scanned 32 tokens at a time so that dt_out / cs_out are written as full 128-byte
+// lines.  grid (nchunks, ceil(H/64), batch), 256 threads.  168 MB of traffic at 128K tokens x 128 heads.
+__global__ void __launch_bounds__(256)
+ssd_dt_cumsum_bf16x2_kernel(const __nv_bfloat16* __restrict__ dt, const float* __restrict__ A,
+                            const float* __restrict__ dt_bias, float* __restrict__ dt_out, float* __restrict__ cs_out,
+                            int L, int H, int Q, int nchunks, int64_t dbs, int64_t dss, int softplus, float dt_min,
+                            float dt_max) {
+  extern __shared__ float sm[];  // [2][Q][33]
+  const int c = blockIdx.x, h0 = blockIdx.y * 64, b = blockIdx.z;
+  const int t0 = c * Q;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sm1 = sm + Q * 33;
+  {
+    const int h = h0 + 2 * lane;                      // H is even on this path
+    const bool hv = h < H;
+    const float b0 = (dt_bias != nullptr && hv) ? dt_bias[h] : 0.f, b1 = (dt_bias != nullptr && hv) ? dt_bias[h + 1] : 0.f;
+    const __nv_bfloat16* src = dt + b * dbs + h;
+    for (int q = warp; q < Q; q += 8) {
+      float v0 = 0.f, v1 = 0.f;
+      if (hv && t0 + q < L) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(src + (int64_t)(t0 + q) * dss);
+        v0 = __uint_as_float(w << 16) + b0;
+        v1 = __uint_as_float(w & 0xffff0000u) + b1;
+        if (softplus && v0 <= 20.f) v0 = log1pf(expf(v0));
+        if (softplus && v1 <= 20.f) v1 = log1pf(expf(v1));
+        v0 = fminf(fmaxf(v0, dt_min), dt_max);
+        v1 = fminf(fmaxf(v1, dt_min), dt_max);
+      }
+      sm[q * 33 + lane] = v0;
+      sm1[q * 33 + lane] = v1;
+    }
+  }
+  __syncthreads();
+  for (int hh = warp; hh < 64 && h0 + hh < H; hh += 8) {
+    const float a = A[h0 + hh];
+    const float* plane = (hh & 1) ? sm1 : sm;
+    const int col = hh >> 1;
+    const int64_t base = (((int64_t)b * nchunks + c) * H + h0 + hh) * Q;
+    float carry = 0.f;
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+      const float v = plane[(q0 + lane) * 33 + col];
+      float incl = v * a;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      dt_out[base + q0 + lane] = v;
+      cs_out[base + q0 + lane] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Register-tiled smem GEMM: acc[i][j] += sum_k A[k][ty+16i] * B[k][tx+16j]   (256 threads = 16 x 16)
 // ---------------------------------------------------------------------------------------------
@@ -330,7 +386,16 @@ int launch_dt_cumsum(const tv_ssd_params& p, float* dt_act, float* cs, cudaStrea
   const int Q = p.chunk_size, H = p.nheads, L = p.seqlen;
   const int nchunks = (int)ceil_div(L, Q);
   dim3 grid(nchunks, (unsigned)ceil_div(H, 32), p.batch);
-  if (p.dtype == TV_BF16)
+  if (p.dtype == TV_BF16 && p.dt_head_stride == 1 && H % 2 == 0 && Q % 32 == 0 && p.dt_seq_stride % 2 == 0 &&
+      p.dt_batch_stride % 2 == 0 && ((uintptr_t)p.dt & 3) == 0) {
+    dim3 grid2(nchunks, (unsigned)ceil_div(H, 64), p.batch);
+    if (2 * Q * 33 * sizeof(float) > 48 * 1024)
+      TV_CUDA_OK(cudaFuncSetAttribute(ssd_dt_cumsum_bf16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(2 * Q * 33 * sizeof(float))));
+    ssd_dt_cumsum_bf16x2_kernel<<<grid2, 256, 2 * Q * 33 * sizeof(float), s>>>(
+        (const __nv_bfloat16*)p.dt, p.A, p.dt_bias, dt_act, cs, L, H, Q, nchunks, p.dt_batch_stride, p.dt_seq_stride,
+        p.dt_softplus, p.dt_min, p.dt_max);
+  } else if (p.dtype == TV_BF16)
     ssd_dt_cumsum_kernel<__nv_bfloat16><<<grid, 128, Q * 33 * sizeof(float), s>>>(
         (const __nv_bfloat16*)p.dt, p.A, p.dt_bias, dt_act, cs, L, H, Q, nchunks, p.dt_batch_stride,
         p.dt_seq_stride, p.dt_head_stride, p.dt_softplus, p.dt_min, p.dt_max);
