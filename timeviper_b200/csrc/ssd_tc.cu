@@ -14,13 +14,14 @@
 //   O: Yo[m,p]   = sum_n C[m,n] S_c[n,p]          (S_c = state entering the chunk, bf16 copy in smem)
 //   S: S_{c+1}   = exp(cs_last) * S_c + sum_k B[k,n] * (dt_k exp(cs_last - cs_k) x[k,p])
 //                  decay: WG_B TMEM -> regs -> TMEM; the sum: tcgen05 SS accumulating onto it
-//      y[m,p]    = Yd + exp(cs_m) * Yo + D * x[m,p]   [* silu(z)]         WG_B epilogue -> global
+//      y[m,p]    = Yd + exp(cs_m) * Yo + D * x[m,p]   [* silu(z)]         WG_C: TMEM -> regs -> bf16 tile staged in the
+//                                                                         dead x stage -> TMA tensor store
 // Decay, mask and cumsum stay in fp32 registers; only the four contractions touch the tensor cores.
 //
 // Warp roles (576 threads): warps 0-3 = WG_A and 4-7 = WG_H (build M), warps 8-11 = WG_B (x scaling, state decay,
 // bf16 state copy), warps 12-15 = WG_C (epilogue), warp 16 = TMA producer, warp 17 =
-// MMA issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers so each is released as soon as
-// its last MMA has been issued.  Tensor-pipe order per iteration is S(c), O(c), D(c), G(c+1).
+// MMA issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers; B and C are released as soon as
+// their last MMA has completed, the x stage once TMA has read the y tile the epilogue staged in it.  Tensor-pipe order per iteration is S(c), O(c), D(c), G(c+1).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "ssd.h"
@@ -56,7 +57,7 @@ constexpr uint32_t T_CB = 0, T_M0 = 128, T_M1 = 192, T_YD = 256, T_YO = 336, T_S
 enum Bar { FULLB0 = 0, FULLB1, EMPTYB0, EMPTYB1, FULLC0, FULLC1, EMPTYC0, EMPTYC1, FULLX0, FULLX1, EMPTYX0, EMPTYX1,
            CBFULL, CBEMPTY, MFULL0, MFULL1, FRDY0, FRDY1, XSFULL, SDECAY, SFULL, STDONE, YOFFDONE, YFULL, YEMPTY, NBAR };
 
-struct Maps { CUtensorMap x, b, c; };
+struct Maps { CUtensorMap x, b, c, y; };
 
 struct Args {
   const float* dt_act; const float* cs;            // (b, nchunks, H, Q) fp32
@@ -172,7 +173,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[FULLB0 + i], 1); mbar_init(&bars[FULLC0 + i], 1); mbar_init(&bars[FULLX0 + i], 1);
       mbar_init(&bars[EMPTYB0 + i], 1); mbar_init(&bars[EMPTYC0 + i], 1);
-      mbar_init(&bars[EMPTYX0 + i], FULL ? (DFOLD ? 9 : 13) : 4);   // one lane per consumer warp + the D(c) commit
+      mbar_init(&bars[EMPTYX0 + i], FULL ? 9 : 4);   // one lane per WG_A and WG_B warp + the epilogue's y-store thread
       mbar_init(&bars[MFULL0 + i], 8); mbar_init(&bars[FRDY0 + i], 4);
     }
     mbar_init(&bars[CBFULL], 1); mbar_init(&bars[CBEMPTY], 8);
@@ -196,7 +197,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       prefetch_tmap(&maps.x); prefetch_tmap(&maps.b);
-      if (FULL) prefetch_tmap(&maps.c);
+      if (FULL) { prefetch_tmap(&maps.c); prefetch_tmap(&maps.y); }
       const bool group_leader = (h % hpg) == 0;      // one CTA per group warms L2 with the shared B / C tiles
       auto l2_prefetch = [&](int c) {
         const int t0 = c * Q;
@@ -335,8 +336,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) umma_ts(tmem + T_YD, tmA + j * 8, umma_desc_advance(dx, j * 32), ID_Y, j > 0);
           }
-          umma_commit(&bars[YFULL]);
-          umma_commit(&bars[EMPTYX0 + s]);
+          umma_commit(&bars[YFULL]);                 // the x stage is released by the epilogue (it stages y in it)
           // ---- G(c+1)
           if (c + 1 < n) issue_cb(c + 1);
         }
@@ -511,8 +511,14 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       const float* sD = reinterpret_cast<const float*>(smem + OFF_D);
       for (int c = 0; c < n; ++c) {
         const int s = c & 1, u = c >> 1;
-        const uint8_t* xst = smem + OFF_X + s * XSTAGE;
+        uint8_t* xst = smem + OFF_X + s * XSTAGE;
         const int t = c * Q + r;
+        // y(c-1) was staged in the other x stage and handed to TMA: once TMA has read it, that stage goes back to the
+        // producer (this replaces the D(c-1) commit; waiting here costs nothing, YFULL(c) is still far away)
+        if (c > 0) {
+          if (threadIdx.x == W_C * 32) { tma_store_wait_read(); mbar_arrive(&bars[EMPTYX0 + (s ^ 1)]); }
+          __syncwarp();
+        }
         float e_r;
         if (!DFOLD) {
           mbar_wait(&bars[FULLX0 + s], u & 1);
@@ -521,7 +527,6 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           e_r = __expf(a.cs[(row0 + (int64_t)c * a.H) * Q + r]);   // one coalesced 512-byte row per chunk (L2 hit)
         }
         const __nv_bfloat16* zrow = HAS_Z ? a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs : nullptr;
-        __nv_bfloat16* orow = a.out + (((int64_t)b * a.L + t) * a.H + h) * P;
         mbar_wait(&bars[YFULL], c & 1);
         tc_fence_after();
         if (r == 0) TV_TRACE(11, c);
@@ -564,7 +569,12 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
             if (HAS_Z) { y0 *= zv[2 * j]; y1 *= zv[2 * j + 1]; }
             pk[j] = pack_bf16x2(y0, y1);
           }
-          if (t < a.L && !TV_ABLATE(11)) st_global_v8(orow + pc * 16, pk);
+          // stage the bf16 row piece in the (dead) x tile of this chunk, same SW32 atom layout: 160 conflict-free
+          // wavefronts per chunk instead of 640 scattered 32-byte global stores; TMA writes it out and clips the tail
+          if (!TV_ABLATE(11)) {
+            *reinterpret_cast<uint4*>(xst + off_sw32(r, 2 * pc)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(xst + off_sw32(r, 2 * pc + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
         };
         if (TV_ABLATE(0)) {
           tc_fence_before();
@@ -593,10 +603,19 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
             if (lane == 0) mbar_arrive(&bars[YEMPTY]);
           }
         }
-        if (!DFOLD) { __syncwarp(); if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]); }
+        fence_proxy_async();                         // the staged tile becomes visible to the async proxy (TMA)
+        named_bar_sync(2, 128);
+        if (threadIdx.x == W_C * 32) {
+          if (!TV_ABLATE(11)) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) tma_store_4d(&maps.y, xst + i * 4096, 16 * i, h, c * Q, b);
+          }
+          tma_store_commit();
+        }
         if (r == 0) TV_TRACE(12, c);
         if (r == 0) TV_TRACE(13, c);
       }
+      if (threadIdx.x == W_C * 32) tma_store_wait_all();
     }
   }
   tc_fence_before();
@@ -842,8 +861,16 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
         set_error("ssd(tcgen05): cuTensorMapEncodeTiled(C) failed");
         return TV_ERR_CUDA;
       }
+      const uint64_t dy[4] = {(uint64_t)P, (uint64_t)p.nheads, L, (uint64_t)p.batch};
+      const uint64_t sy[3] = {(uint64_t)P * 2, (uint64_t)p.nheads * P * 2, (uint64_t)L * p.nheads * P * 2};
+      const uint32_t by[4] = {16, 1, (uint32_t)Q, 1};
+      if (!encode_bf16_tmap(&maps.y, p.out, 4, dy, sy, by, CU_TENSOR_MAP_SWIZZLE_32B)) {
+        set_error("ssd(tcgen05): cuTensorMapEncodeTiled(out) failed");
+        return TV_ERR_CUDA;
+      }
     } else {
       maps.c = maps.b;
+      maps.y = maps.b;
     }
   }
   Args a;
