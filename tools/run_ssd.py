@@ -19,6 +19,16 @@ for _ in range(iters):
     tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, dt_bias=dt_bias, dt_softplus=True, return_final_states=True)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
+zms = None
+if os.environ.get("TV_RUN_Z"):
+    for _ in range(2):
+        tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, z=z, dt_bias=dt_bias, dt_softplus=True, return_final_states=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, z=z, dt_bias=dt_bias, dt_softplus=True, return_final_states=True)
+    e1.record(); torch.cuda.synchronize()
+    print(f"with z gating fused in the epilogue: {e0.elapsed_time(e1) / iters:.3f} ms")
 print(f"L={L} H={H} G={G} ssd {ms:.3f} ms  {(45312/128*H)*L/ms/1e6:.1f} GB/s  {ms*1e3/ (L/128):.2f} us/chunk")
 # shard summary (pass 1 of the sequence-sharded path)
 for scale, tag in ((1.0, "fast decay (A = -1..-H)"), (1e-4, "slow decay (A * 1e-4: every chunk contributes)")):
