@@ -8,7 +8,8 @@
 // Roofline: pure HBM streaming, 2 * dim * sizeof(T) bytes per token (49,152 B at dim 12288, bf16).
 // Layout/tiling: one thread owns 16 bytes of channels (8 bf16 / 4 fp32) and walks TOK consecutive tokens with the
 // K-1 previous rows kept in registers, so every x element is read once per CTA (halo re-read = (K-1)/tok, served
-// from L2); a warp reads/writes 512 contiguous bytes per token row.
+// from L2); a warp reads/writes 512 contiguous bytes per token row.  Input rows are prefetched with cp.async (16 bytes
+// per thread) into a per-thread ring in shared memory, so the bytes in flight are not bounded by registers.
 #include "common.cuh"
 
 namespace tv {
@@ -17,11 +18,24 @@ namespace tv {
 #define TV_CONV_THREADS 32     // one warp per CTA: 16 CTAs/SM by registers; measured 81.5 % vs 80.2 % with 128-thread CTAs
 #endif
 constexpr int CONV_THREADS = TV_CONV_THREADS;
-// Tokens per CTA along the sequence (a template argument): longer runs amortise the weight / halo prologue (measured
-// at 128K tokens: 64 -> 77%, 128 -> 80%, 256 -> 81% of the HBM peak), shorter ones keep enough CTAs for short shards.
-constexpr int CONV_TOK_LONG = 128, CONV_TOK_SHORT = 64;
+#ifndef TV_CONV_RING
+#define TV_CONV_RING 16         // depth of the per-thread cp.async row ring in shared memory
+#endif
+#ifndef TV_CONV_MINWARPS
+#define TV_CONV_MINWARPS 16     // resident warps per SM the register allocation must allow
+#endif
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+// Tokens per CTA along the sequence.  Measured at 128K tokens with the cp.async ring (% of the HBM copy peak):
+// 32 -> 94.0, 48 -> 99.5, 64 -> 98.4, 128 -> 97.1, 256 -> 96.1, 512 -> 94.1; at 16K tokens 48 and 64 tie (87.5).
+#ifndef TV_CONV_TOK
+#define TV_CONV_TOK 48
+#endif
+constexpr int CONV_TOK = TV_CONV_TOK;
 // channels per thread = one 16-byte access: 8 (bf16) / 4 (fp32); a warp covers 512 contiguous bytes per token row
-constexpr int CONV_U = 8;      // independent row loads in flight per thread (kept as raw words until used)
 
 template <typename T> struct Raw4 {   // register image of one 16-byte access
   uint4 r;
@@ -30,10 +44,11 @@ template <typename T> struct Raw4 {   // register image of one 16-byte access
   static __device__ __forceinline__ void store(T* p, const float (&v)[Vec16<T>::N]) { store16<T>(p, v); }
 };
 
-// <= 128 registers per thread => 4 CTAs (16 warps) per SM, each thread keeping CONV_U raw row loads in flight:
-// 16 warps * 8 loads * 512 B = 64 KB in flight per SM, above the ~45 KB that 6.5 TB/s needs at ~1 us latency.
-template <typename T, int K, bool SILU, int TOK>
-__global__ void __launch_bounds__(128, 4)
+// 16 resident warps per SM, each thread keeping TV_CONV_RING = 16 row loads in flight through its shared-memory ring:
+// 16 warps * 16 rows * 512 B = 128 KB in flight (and of shared memory) per SM.  Measured at 128K tokens: 97 % of the HBM
+// peak (the register-prefetch version with 8 rows in flight per thread reached 81 %; ring depth 8 -> 89 %, 12 -> 96 %).
+template <typename T, int K, bool SILU>
+__global__ void __launch_bounds__(CONV_THREADS, TV_CONV_MINWARPS * 32 / CONV_THREADS)
 conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T* __restrict__ bias,
                   const T* __restrict__ init, T* __restrict__ out, T* __restrict__ fin,
                   int dim, int L, int64_t xbs, int64_t xss, int64_t obs, int64_t oss) {
@@ -42,8 +57,8 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
   const int c0 = (blockIdx.x * CONV_THREADS + threadIdx.x) * V;
   if (c0 >= dim) return;
   const int b = blockIdx.z;
-  const int t0 = blockIdx.y * TOK;
-  const int t1 = min(t0 + TOK, L);
+  const int t0 = blockIdx.y * CONV_TOK;
+  const int t1 = min(t0 + CONV_TOK, L);
   x += (int64_t)b * xbs + c0;
   out += (int64_t)b * obs + c0;
 
@@ -79,40 +94,48 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
     for (int v = 0; v < V2; ++v) win[j][v] = make_float2(tmp[2 * v], tmp[2 * v + 1]);
   }
 
-  for (int tt = t0; tt < t1; tt += CONV_U) {
-    Raw4<T> xin[CONV_U];
+  // Row prefetch through shared memory: every thread keeps D rows (16 bytes each) in flight with cp.async into its own
+  // ring slots (a warp's slots of one depth are 512 contiguous bytes), so the bytes in flight are not bounded by registers.
+  constexpr int D = TV_CONV_RING;
+  extern __shared__ uint4 ring_[];
+  uint4* my = ring_ + ((threadIdx.x >> 5) * D) * 32 + (threadIdx.x & 31);
 #pragma unroll
-    for (int u = 0; u < CONV_U; ++u)
-      if (tt + u < t1) xin[u].load(x + (int64_t)(tt + u) * xss);
+  for (int d = 0; d < D; ++d) {
+    if (t0 + d < t1) cp_async16(my + d * 32, x + (int64_t)(t0 + d) * xss);
+    cp_async_commit();
+  }
+  int slot = 0;
+#pragma unroll 4
+  for (int tt = t0; tt < t1; ++tt) {
+    cp_async_wait<D - 1>();
+    const uint4 raw = my[slot * 32];
+    float xf[V], o[V];
+    unpack16<T>(raw, xf);
 #pragma unroll
-    for (int u = 0; u < CONV_U; ++u) {
-      if (tt + u < t1) {
-        float xf[V], o[V];
-        xin[u].unpack(xf);
+    for (int v = 0; v < V2; ++v) {
+      const float2 xv = make_float2(xf[2 * v], xf[2 * v + 1]);
+      float2 acc = bv[v];
 #pragma unroll
-        for (int v = 0; v < V2; ++v) {
-          const float2 xv = make_float2(xf[2 * v], xf[2 * v + 1]);
-          float2 acc = bv[v];
-#pragma unroll
-          for (int k = 0; k < K - 1; ++k) acc = __ffma2_rn(w[k][v], win[k][v], acc);
-          acc = __ffma2_rn(w[K - 1][v], xv, acc);
-          if (SILU) {
-            if (FAST) {    // x / (1 + 2^(-x log2 e)) with packed scale / add / multiply around the two MUFU pairs
-              const float2 tneg = __fmul2_rn(acc, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-              const float2 d = __fadd2_rn(make_float2(ex2_approx_f(tneg.x), ex2_approx_f(tneg.y)), make_float2(1.f, 1.f));
-              acc = __fmul2_rn(acc, make_float2(rcp_approx_f(d.x), rcp_approx_f(d.y)));
-            } else {
-              acc = make_float2(silu<false>(acc.x), silu<false>(acc.y));
-            }
-          }
-          o[2 * v] = acc.x; o[2 * v + 1] = acc.y;
-#pragma unroll
-          for (int k = 0; k < K - 2; ++k) win[k][v] = win[k + 1][v];
-          win[K - 2][v] = xv;
+      for (int k = 0; k < K - 1; ++k) acc = __ffma2_rn(w[k][v], win[k][v], acc);
+      acc = __ffma2_rn(w[K - 1][v], xv, acc);
+      if (SILU) {
+        if (FAST) {
+          const float2 tneg = __fmul2_rn(acc, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+          const float2 d = __fadd2_rn(make_float2(ex2_approx_f(tneg.x), ex2_approx_f(tneg.y)), make_float2(1.f, 1.f));
+          acc = __fmul2_rn(acc, make_float2(rcp_approx_f(d.x), rcp_approx_f(d.y)));
+        } else {
+          acc = make_float2(silu<false>(acc.x), silu<false>(acc.y));
         }
-        Raw4<T>::store(out + (int64_t)(tt + u) * oss, o);
       }
+      o[2 * v] = acc.x; o[2 * v + 1] = acc.y;
+#pragma unroll
+      for (int k = 0; k < K - 2; ++k) win[k][v] = win[k + 1][v];
+      win[K - 2][v] = xv;
     }
+    if (tt + D < t1) cp_async16(my + slot * 32, x + (int64_t)(tt + D) * xss);   // refill the slot just consumed
+    cp_async_commit();
+    slot = slot + 1 == D ? 0 : slot + 1;
+    Raw4<T>::store(out + (int64_t)tt * oss, o);
   }
 
   // carried-out state = the last K-1 input columns (includes carried-in columns when L < K-1)
@@ -128,14 +151,9 @@ conv1d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ weight, const T
 template <typename T, int K>
 static int launch_conv(const tv_conv1d_params& p, cudaStream_t s) {
   constexpr int V = Vec16<T>::N;
-  // long runs only when they still leave >= 8 waves of CTAs (148 SMs x 4 resident)
-  const int64_t xblocks = ceil_div(p.dim / V, CONV_THREADS);
-  const int tok = xblocks * ceil_div(p.seqlen, CONV_TOK_LONG) * p.batch >= 8 * 148 * 4 ? CONV_TOK_LONG : CONV_TOK_SHORT;
-  dim3 grid((unsigned)xblocks, (unsigned)ceil_div(p.seqlen, tok), p.batch);
-  auto kern = tok == CONV_TOK_LONG
-                  ? (p.silu ? conv1d_fwd_kernel<T, K, true, CONV_TOK_LONG> : conv1d_fwd_kernel<T, K, false, CONV_TOK_LONG>)
-                  : (p.silu ? conv1d_fwd_kernel<T, K, true, CONV_TOK_SHORT> : conv1d_fwd_kernel<T, K, false, CONV_TOK_SHORT>);
-  kern<<<grid, CONV_THREADS, 0, s>>>((const T*)p.x, (const T*)p.weight, (const T*)p.bias,
+  dim3 grid((unsigned)ceil_div(p.dim / V, CONV_THREADS), (unsigned)ceil_div(p.seqlen, CONV_TOK), p.batch);
+  auto kern = p.silu ? conv1d_fwd_kernel<T, K, true> : conv1d_fwd_kernel<T, K, false>;
+  kern<<<grid, CONV_THREADS, (size_t)(CONV_THREADS / 32) * TV_CONV_RING * 512, s>>>((const T*)p.x, (const T*)p.weight, (const T*)p.bias,
                                      (const T*)p.initial_states, (T*)p.out, (T*)p.final_states, p.dim,
                                      p.seqlen, p.x_batch_stride, p.x_seq_stride, p.out_batch_stride,
                                      p.out_seq_stride);
