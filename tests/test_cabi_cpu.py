@@ -136,3 +136,22 @@ def test_patch_reference_on_the_real_module():
     finally:
         for k, v in saved.items():
             setattr(mn, k, v)
+
+
+def test_streamed_prefill_segment_schedule():
+    """Host logic of prefill_from_host: segments tile [0, L) exactly, every boundary but the end is a chunk multiple
+    (the SSD state and conv halo are carried across them), no segment exceeds the buffer, and long inputs ramp up /
+    down so that the un-overlapped first H2D and last D2H copies are short."""
+    import random
+    from timeviper_b200.mixer import Mamba2MixerPrefill as M
+    rnd = random.Random(0)
+    cases = [(131072, 16384), (1000, 256), (300, 128), (5, 128), (128, 128), (70000, 16384)]
+    cases += [(rnd.randint(1, 200000), rnd.choice([128, 256, 1024, 4096, 16384])) for _ in range(500)]
+    for L, seg in cases:
+        b = M._segment_bounds(L, seg, 128)
+        sizes = [b1 - b0 for b0, b1 in zip(b, b[1:])]
+        assert b[0] == 0 and b[-1] == L and all(n > 0 for n in sizes)
+        assert all(x % 128 == 0 for x in b[:-1])
+        assert max(sizes) <= seg + 127
+    b = M._segment_bounds(131072, 16384, 128)
+    assert b[1] == 2048 and b[-1] - b[-2] == 2048

@@ -672,33 +672,41 @@ ssd_suffix_scan_kernel(const float* __restrict__ cs, float* __restrict__ logdeca
 
 namespace st {
 constexpr int THREADS = 192;                     // warps 0-3: x scaling, warp 4: TMA producer, warp 5: MMA issuer
-constexpr int NST = 3;                            // B / x stages: TMA latency (~2000 cycles) x 54 KB per chunk needs depth
-constexpr uint32_t OFF_B = 0, OFF_X = NST * tc::TILE_BC, OFF_XS = OFF_X + NST * tc::XSTAGE;
-constexpr uint32_t OFF_BAR = OFF_XS + 2 * tc::TILE_X;
+// Two stages of (B tile | x tile): 109 KB, so that TWO CTAs fit on an SM -- the walk over the chunks of one head is
+// a latency chain (TMA -> scale -> MMA), and a second resident CTA (the other half of the same head's chunks, see
+// `split`) fills its bubbles.  w*x is written back IN PLACE over the x tile (nothing else reads raw x here).
+constexpr int NST = 2;
+constexpr uint32_t OFF_B = 0, OFF_X = NST * tc::TILE_BC;
+constexpr uint32_t OFF_BAR = OFF_X + NST * tc::XSTAGE;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;
-enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NST, XSFULL0 = EMPTY0 + NST, XSEMPTY0 = XSFULL0 + 2, DONE = XSEMPTY0 + 2, NBAR };
-static_assert(OFF_X % 1024 == 0 && SMEM_BYTES <= kMaxDynSmem, "state kernel smem");
-static_assert(OFF_XS % 1024 == 0, "tile alignment");
+enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NST, SCALED0 = EMPTY0 + NST, DONE = SCALED0 + NST, NBAR };
+static_assert(OFF_X % 1024 == 0 && 2 * SMEM_BYTES <= 226 * 1024, "state kernel smem: two CTAs per SM");
 }  // namespace st
 
-__global__ void __launch_bounds__(st::THREADS, 1)
-ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const int* __restrict__ first_chunk) {
+// grid (H, batch, split).  Part z of `split` handles the visited-chunk indices [count*z/split, count*(z+1)/split) of the
+// backwards walk n-1, n-2, ..., c_first; because the decay is taken relative to the END of the shard the partial states
+// simply add up: with split == 2 both parts red.add onto a zeroed output (two addends: order-independent, bit-stable).
+__global__ void __launch_bounds__(st::THREADS, 2)
+ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const int* __restrict__ first_chunk,
+                 const int split) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + st::OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + st::OFF_BAR + st::NBAR * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int h = blockIdx.x, b = blockIdx.y, part = blockIdx.z;
   const int g = h / (a.H / a.G);
   const int n = a.nchunks;
   const int c_first = first_chunk[(int64_t)b * a.H + h];
-  const int count = n - c_first;                       // chunks n-1, n-2, ..., c_first
+  const int total = n - c_first;                       // chunks n-1, n-2, ..., c_first
+  const int i_begin = (int)((int64_t)total * part / split), i_end = (int)((int64_t)total * (part + 1) / split);
+  const int count = i_end - i_begin;
+  if (count == 0 && split > 1) return;                 // nothing to add (the output was zeroed by the host)
   if (threadIdx.x == 0) {
     for (int i = 0; i < st::NST; ++i) {
-      mbar_init(&bars[st::FULL0 + i], 1); mbar_init(&bars[st::EMPTY0 + i], 5);      // 4 scaling warps + the MMA commit
+      mbar_init(&bars[st::FULL0 + i], 1); mbar_init(&bars[st::EMPTY0 + i], 1); mbar_init(&bars[st::SCALED0 + i], 4);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars[st::XSFULL0 + i], 4); mbar_init(&bars[st::XSEMPTY0 + i], 1); }
     mbar_init(&bars[st::DONE], 1);
     fence_mbar_init();
   }
@@ -712,9 +720,9 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
   if (warp == 4) {
     if (elect_one()) {
       prefetch_tmap(&maps.x); prefetch_tmap(&maps.b);
-      for (int i = 0; i < count; ++i) {
-        const int c = n - 1 - i, s = i % st::NST, u = i / st::NST;
-        if (i >= st::NST) mbar_wait(&bars[st::EMPTY0 + s], (u - 1) & 1);
+      for (int j = 0; j < count; ++j) {
+        const int c = n - 1 - (i_begin + j), s = j % st::NST, u = j / st::NST;
+        if (j >= st::NST) mbar_wait(&bars[st::EMPTY0 + s], (u - 1) & 1);
         uint8_t* sb = smem + st::OFF_B + s * TILE_BC;
         uint8_t* sx = smem + st::OFF_X + s * XSTAGE;
         mbar_arrive_expect_tx(&bars[st::FULL0 + s], TILE_BC + XSTAGE);
@@ -722,7 +730,7 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
         tma_load_4d(sb, &maps.b, &bars[st::FULL0 + s], 0, g, t0, b);
         tma_load_4d(sb + 16384, &maps.b, &bars[st::FULL0 + s], 64, g, t0, b);
 #pragma unroll
-        for (int j = 0; j < 5; ++j) tma_load_4d(sx + j * 4096, &maps.x, &bars[st::FULL0 + s], 16 * j, h, t0, b);
+        for (int k = 0; k < 5; ++k) tma_load_4d(sx + k * 4096, &maps.x, &bars[st::FULL0 + s], 16 * k, h, t0, b);
         bulk_load(sx + TILE_X, a.cs + (row0 + (int64_t)c * a.H) * Q, 512, &bars[st::FULL0 + s]);
         bulk_load(sx + TILE_X + 512, a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512, &bars[st::FULL0 + s]);
       }
@@ -732,30 +740,32 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
       constexpr uint32_t ID_ST = umma_idesc_bf16(128, P, true, true);
       const uint32_t sbase = smem_u32(smem);
       const uint64_t dB = umma_smem_desc(sbase + st::OFF_B, 16384, 1024, SWZ_128B);
-      const uint64_t dXS = umma_smem_desc(sbase + st::OFF_XS, 4096, 256, SWZ_32B);
+      const uint64_t dXS = umma_smem_desc(sbase + st::OFF_X, 4096, 256, SWZ_32B);
 #pragma unroll 1
-      for (int i = 0; i < count; ++i) {
-        const int s = i % st::NST, u = i / st::NST, xb = i & 1, xu = i >> 1;
-        mbar_wait(&bars[st::FULL0 + s], u & 1);
-        mbar_wait(&bars[st::XSFULL0 + xb], xu & 1);
+      for (int j = 0; j < count; ++j) {
+        const int s = j % st::NST, u = j / st::NST;
+        mbar_wait(&bars[st::SCALED0 + s], u & 1);       // implies FULL: the scaling warps waited for the tiles
         tc_fence_after();
         const uint64_t db = umma_desc_advance(dB, (uint32_t)(s * (TILE_BC >> 4)));
-        const uint64_t dx = umma_desc_advance(dXS, (uint32_t)(xb * (TILE_X >> 4)));
+        const uint64_t dx = umma_desc_advance(dXS, (uint32_t)(s * (XSTAGE >> 4)));
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_ss(tmem, umma_desc_advance(db, j * 128), umma_desc_advance(dx, j * 32), ID_ST, (i > 0 || j > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem, umma_desc_advance(db, k * 128), umma_desc_advance(dx, k * 32), ID_ST, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&bars[st::EMPTY0 + s]);
-        umma_commit(&bars[st::XSEMPTY0 + xb]);
       }
       umma_commit(&bars[st::DONE]);
     }
   } else {
-    // ---- x scaling: xs[k,p] = x[k,p] * dt_k * exp(cs_last - cs_k + T_c), T_c = totals of the chunks already visited
+    // ---- x scaling in place: x[k,p] *= dt_k * exp(cs_last - cs_k + T_c), T_c = totals of the chunks already visited
     const int r = threadIdx.x;
     float T = 0.f;
-    for (int i = 0; i < count; ++i) {
-      const int s = i % st::NST, u = i / st::NST, xb = i & 1, xu = i >> 1;
-      const uint8_t* xst = smem + st::OFF_X + s * XSTAGE;
+    if (i_begin > 0) {                                   // totals of the chunks the earlier part(s) visit
+      for (int i = lane; i < i_begin; i += 32) T += a.cs[(row0 + (int64_t)(n - 1 - i) * a.H) * Q + (Q - 1)];
+      T = warp_sum(T);
+    }
+    for (int j = 0; j < count; ++j) {
+      const int s = j % st::NST, u = j / st::NST;
+      uint8_t* xst = smem + st::OFF_X + s * XSTAGE;
       const float* sCS = reinterpret_cast<const float*>(xst + TILE_X);
       const float* sDT = sCS + 128;
       mbar_wait(&bars[st::FULL0 + s], u & 1);
@@ -763,19 +773,17 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
       const float w_r = sDT[r] * __expf(cs_last - sCS[r] + T);
       T += cs_last;
       const __nv_bfloat162 w2 = __float2bfloat162_rn(w_r);
-      if (i >= 2) mbar_wait(&bars[st::XSEMPTY0 + xb], (xu - 1) & 1);
-      uint8_t* xs_out = smem + st::OFF_XS + xb * TILE_X;
 #pragma unroll
       for (int q = 0; q < 10; ++q) {
         uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, q));
         __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hv[j] = __hmul2(hv[j], w2);
-        *reinterpret_cast<uint4*>(xs_out + off_sw32(r, q)) = v;
+        for (int k = 0; k < 4; ++k) hv[k] = __hmul2(hv[k], w2);
+        *reinterpret_cast<uint4*>(xst + off_sw32(r, q)) = v;
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&bars[st::XSFULL0 + xb]); mbar_arrive(&bars[st::EMPTY0 + s]); }
+      if (lane == 0) mbar_arrive(&bars[st::SCALED0 + s]);
     }
     mbar_wait(&bars[st::DONE], 0);
     tc_fence_after();
@@ -783,11 +791,18 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
 #pragma unroll
     for (int pc = 0; pc < 5; ++pc) {
       uint32_t v[16];
-      tmem_ld16(tmem + lane_base + pc * 16, v);
-      tmem_ld_wait();
+      if (count > 0) {
+        tmem_ld16(tmem + lane_base + pc * 16, v);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        a.fin[(((int64_t)b * a.H + h) * P + pc * 16 + j) * N + r] = __uint_as_float(v[j]);
+        for (int k = 0; k < 16; ++k) v[k] = 0u;       // split == 1 and no live chunk: the summary is exactly zero
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float* dst = &a.fin[(((int64_t)b * a.H + h) * P + pc * 16 + k) * N + r];
+        if (split > 1) atomicAdd(dst, __uint_as_float(v[k])); else *dst = __uint_as_float(v[k]);
+      }
     }
   }
   tc_fence_before();
@@ -894,7 +909,11 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
     ssd_suffix_scan_kernel<<<(BH + 3) / 4, 128, 0, s>>>(cs, p.logdecay_sum, first_chunk, BH, p.nheads, nchunks, Q);
     TV_CUDA_OK(cudaGetLastError());
     TV_CUDA_OK(cudaFuncSetAttribute(ssd_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st::SMEM_BYTES));
-    ssd_state_kernel<<<grid, st::THREADS, st::SMEM_BYTES, s>>>(maps, a, first_chunk);
+    // two CTAs per head (each half of the chunk walk) once the walk is long enough to pay for zeroing the output
+    const int split = nchunks >= 16 ? 2 : 1;
+    if (split > 1)
+      TV_CUDA_OK(cudaMemsetAsync(p.final_states, 0, (size_t)p.batch * p.nheads * P * N * sizeof(float), s));
+    ssd_state_kernel<<<dim3(p.nheads, p.batch, split), st::THREADS, st::SMEM_BYTES, s>>>(maps, a, first_chunk, split);
     lrc = TV_OK;
   }
   else if (p.z != nullptr) lrc = dfold ? launch(ssd_fused_kernel<true, true, true>) : launch(ssd_fused_kernel<true, true, false>);

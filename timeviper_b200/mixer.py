@@ -130,6 +130,25 @@ class Mamba2MixerPrefill(nn.Module):
             return (scan_output, ssm_state, conv_final) if return_conv_state else (scan_output, ssm_state)
         return scan_output
 
+    @staticmethod
+    def _segment_bounds(L, seg, chunk):
+        """Token boundaries of the streamed segments: seg/8, seg/4, seg/2, seg, ..., seg, seg/2, seg/4, seg/8 (each a
+        multiple of `chunk`, except that the last one takes the ragged remainder)."""
+        ramp = [max(chunk, (seg >> k) // chunk * chunk) for k in (3, 2, 1)]
+        if L < 2 * sum(ramp) + seg:                       # short input: plain equal segments
+            sizes = [seg] * (L // seg) + ([L % seg] if L % seg else [])
+        else:
+            mid = L - 2 * sum(ramp)
+            rem = mid % seg
+            aligned, ragged = rem // chunk * chunk, rem % chunk      # only the very last segment may be ragged
+            sizes = ramp + [seg] * (mid // seg) + ([aligned] if aligned else []) + ramp[::-1]
+            sizes[-1] += ragged
+        bounds = [0]
+        for n in sizes:
+            bounds.append(min(L, bounds[-1] + n))
+        assert bounds[-1] == L and all(b1 > b0 for b0, b1 in zip(bounds, bounds[1:]))
+        return bounds
+
     @torch.no_grad()
     def prefill_from_host(self, hidden_host, out_host=None, segment_tokens=16384, cache_params=None):
         """Prefill a (b, L, hidden) sequence that lives in (pinned) HOST memory and return the mixer output in
@@ -148,16 +167,20 @@ class Mamba2MixerPrefill(nn.Module):
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
-        nseg = (L + seg - 1) // seg
-        d_in = [torch.empty((b, seg, hidden), dtype=hidden_host.dtype, device=dev) for _ in range(2)]
-        d_out = [torch.empty((b, seg, self.hidden_size), dtype=hidden_host.dtype, device=dev) for _ in range(2)]
+        # segment schedule: full-size segments in the middle, geometrically smaller ones at both ends, so that the
+        # un-overlapped pipeline fill (first H2D) and drain (last D2H) copy ~seg/8 tokens instead of seg
+        bounds = self._segment_bounds(L, seg, self.chunk_size)
+        nseg = len(bounds) - 1
+        cap = max(b1 - b0 for b0, b1 in zip(bounds, bounds[1:]))
+        d_in = [torch.empty((b, cap, hidden), dtype=hidden_host.dtype, device=dev) for _ in range(2)]
+        d_out = [torch.empty((b, cap, self.hidden_size), dtype=hidden_host.dtype, device=dev) for _ in range(2)]
         ev_in = [torch.cuda.Event() for _ in range(nseg)]
         ev_cmp = [torch.cuda.Event() for _ in range(nseg)]
         ev_out = [torch.cuda.Event() for _ in range(nseg)]
         conv_state, ssm_state, tail = None, None, None
         K = self.conv_kernel_size
         for i in range(nseg):
-            t0, t1 = i * seg, min((i + 1) * seg, L)
+            t0, t1 = bounds[i], bounds[i + 1]
             n = t1 - t0
             with torch.cuda.stream(s_in):
                 if i >= 2:
