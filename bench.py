@@ -37,7 +37,7 @@ UNIT = "tokens/s"
 BYTES_PER_TOKEN = {"conv1d": 49152, "ssd": 45312, "gated_rmsnorm": 61440}
 # per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from one `ncu --set full` capture of this
 # command at seqlen 131072 on 1 GPU (profiles/r01_summary.md); null for any other configuration
-NCU_TRAFFIC_128K = {"conv1d": 6.572e9, "ssd": 6.194e9, "gated_rmsnorm": 8.026e9}
+NCU_TRAFFIC_128K = {"conv1d": 6.500e9, "ssd": 6.031e9 + 0.111e9, "gated_rmsnorm": 8.028e9}   # ssd = fused + dt/cumsum
 
 
 def peaks():
