@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TV_ABI_VERSION 2
+#define TV_ABI_VERSION 3
 
 typedef enum { TV_F32 = 0, TV_BF16 = 1 } tv_dtype;
 
@@ -142,6 +142,54 @@ int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, cons
                                 float* out, int32_t rank, int32_t batch, int32_t nheads,
                                 int32_t headdim, int32_t dstate, int64_t states_rank_stride,
                                 int64_t logdecay_rank_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Single-token decode step: the two operators the reference's cached branch calls,
+ * modeling_nano.py:495-501 and :528-539, consuming the states the prefill path leaves in the cache.
+ *
+ * causal_conv1d_update (causal_conv1d 1.5.2): conv_state (batch, dim, state_len >= width) is shifted left by one column
+ * in place, x (batch, dim) becomes its last column, out[b,c] = act(bias[c] + sum_k w[c,k] * state[b,c,state_len-width+k]).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;               /* (batch, dim), unit channel stride                              */
+  void* conv_state;            /* (batch, dim, state_len), unit stride on the last dim, in place */
+  const void* weight;          /* (dim, width) contiguous                                        */
+  const void* bias;            /* (dim,) or NULL                                                 */
+  void* out;                   /* (batch, dim), unit channel stride                              */
+  int32_t batch, dim, width, state_len;
+  int64_t x_batch_stride, out_batch_stride, state_batch_stride, state_dim_stride;
+  int32_t silu;
+  int32_t dtype;               /* tv_dtype of x / conv_state / weight / bias / out               */
+} tv_conv1d_update_params;
+
+int tv_causal_conv1d_update(const tv_conv1d_update_params* p, void* stream);
+
+/* selective_state_update (mamba_ssm.ops.triton.selective_state_update), one token:
+ *   dt' = clamp(softplus(dt + dt_bias));  state = state * exp(dt' * A) + dt' * B[g] * x;  out = sum_n state * C[g] + D * x
+ *   [out *= silu(z)],  g = h / (H/G).  state (batch, H, P, N) contiguous, updated in place.
+ * x, dt, z: (batch, H, P); A: (H, P, N); D, dt_bias: (H, P) -- all addressed through element strides, so the expanded
+ * (stride-0) views the reference builds at modeling_nano.py:515-522 are passed as they are.  A, D, dt_bias are f32. */
+typedef struct {
+  void* state;
+  const void* x; const void* dt; const float* A; const void* B; const void* C;
+  const float* D; const void* z; const float* dt_bias;
+  void* out;                   /* (batch, H, P) contiguous                                       */
+  int32_t batch, nheads, headdim, ngroups, dstate;
+  int64_t x_batch_stride, x_head_stride, x_dim_stride;
+  int64_t dt_batch_stride, dt_head_stride, dt_dim_stride;
+  int64_t a_head_stride, a_dim_stride, a_state_stride;
+  int64_t b_batch_stride, b_group_stride;            /* unit stride over the state dim */
+  int64_t c_batch_stride, c_group_stride;
+  int64_t d_head_stride, d_dim_stride;
+  int64_t z_batch_stride, z_head_stride, z_dim_stride;
+  int64_t bias_head_stride, bias_dim_stride;
+  int32_t dt_softplus;
+  float dt_min, dt_max;        /* clamp after softplus; (0, +inf) = none                          */
+  int32_t dtype;               /* tv_dtype of x / dt / B / C / z / out                            */
+  int32_t state_dtype;         /* tv_dtype of state                                               */
+} tv_ssu_params;
+
+int tv_selective_state_update(const tv_ssu_params* p, void* stream);
 
 /* Debug hook (profiling only): device buffer of nchunks*16 int64 that CTA (0,0) of the fused SSD kernel fills
  * with clock64() stamps of its pipeline events; NULL (default) disables it. */

@@ -26,6 +26,10 @@ CASES = {
 }
 
 
+class _ListOnDevice(list):
+    device = torch.device("cpu")
+
+
 def load_reference():
     sys.path.insert(0, os.path.join(HERE, "_shim"))
     sys.path.insert(0, REF)
@@ -54,8 +58,22 @@ def main():
         with torch.no_grad():
             out = mixer(hs, cache_params=cache, cache_position=torch.arange(L))
         blob = {k: v.detach().numpy() for k, v in mixer.state_dict().items()}
+        prefill_conv, prefill_ssm = cache.conv_states[0].clone(), cache.ssm_states[0].clone()
+        # three cached decode steps through the same forward (torch_forward's cache_position > 0 branch, :683-696,
+        # :716-773), continuing from the prefill cache
+        dec_hs = torch.randn(1, 3, hidden)
+        dec_out = []
+        # the cached branch reads `cache_params.ssm_states.device` (:718) although the cache keeps per-layer LISTS
+        # (:237-254), so as shipped it raises AttributeError; the harness gives the lists a .device instead of
+        # touching the reference
+        cache.ssm_states, cache.conv_states = _ListOnDevice(cache.ssm_states), _ListOnDevice(cache.conv_states)
+        with torch.no_grad():
+            for i in range(3):
+                dec_out.append(mixer(dec_hs[:, i:i + 1], cache_params=cache, cache_position=torch.tensor([L + i])))
+        blob.update(decode_hidden_states=dec_hs.numpy(), decode_out=torch.cat(dec_out, dim=1).numpy(),
+                    decode_conv_state=cache.conv_states[0].numpy(), decode_ssm_state=cache.ssm_states[0].numpy())
         blob.update(hidden_states=hs.numpy(), out=out.numpy(),
-                    conv_state=cache.conv_states[0].numpy(), ssm_state=cache.ssm_states[0].numpy(),
+                    conv_state=prefill_conv.numpy(), ssm_state=prefill_ssm.numpy(),
                     dims=np.array([hidden, H, P, G, N, Q, L], dtype=np.int64),
                     time_step_limit=np.array(lim, dtype=np.float64))
         path = os.path.join(out_dir, f"mixer_{name}.npz")

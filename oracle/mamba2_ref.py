@@ -230,6 +230,75 @@ def mixer_forward_ref(p: dict, hidden_states: torch.Tensor, *, num_heads: int, h
 
 
 # --------------------------------------------------------------------------------------------
+# single-token decode step: torch_forward's cached branch, modeling_nano.py:683-696, 716-773;
+# operator contracts of the fast path at :495-539 (causal_conv1d_update, selective_state_update)
+# --------------------------------------------------------------------------------------------
+def causal_conv1d_update_ref(x: torch.Tensor, conv_state: torch.Tensor, weight: torch.Tensor,
+                             bias: Optional[torch.Tensor] = None, activation: Optional[str] = None,
+                             dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x (b, dim) new pre-conv column, conv_state (b, dim, state_len >= K) -> (out (b, dim), new conv_state).
+    The state is shifted left by one column and x appended (:338-344 with cache_init=False); the output is the dot
+    product of its last K columns with the weights (:689-696)."""
+    K = weight.shape[1]
+    new_state = torch.cat([conv_state[..., 1:], x.to(conv_state.dtype)[..., None]], dim=-1)
+    out = (new_state[..., -K:].to(dtype) * weight.to(dtype)).sum(-1)
+    if bias is not None:
+        out = out + bias.to(dtype)
+    if activation in ("silu", "swish"):
+        out = F.silu(out)
+    elif activation is not None:
+        raise ValueError(activation)
+    return out, new_state
+
+
+def selective_state_update_ref(state, x, dt, A, B, C, D=None, z=None, dt_bias=None, dt_softplus=False,
+                               dtype: torch.dtype = torch.float32):
+    """state (b,H,P,N), x (b,H,P), dt (b,H,P), A (H,P,N), B/C (b,G,N), D (H,P), z (b,H,P), dt_bias (H,P)
+    -> (out (b,H,P), new state (b,H,P,N) in ``dtype``).  :716-768; head h reads group h // (H/G) (:740-742)."""
+    b, H, P, N = state.shape
+    G = B.shape[1]
+    dt = dt.to(dtype)
+    if dt_bias is not None:
+        dt = dt + dt_bias.to(dtype)
+    if dt_softplus:
+        dt = torch.where(dt <= 20.0, F.softplus(dt), dt)
+    dA = torch.exp(dt[..., None] * A.to(dtype))                                   # (b,H,P,N)
+    Bh = B.to(dtype).repeat_interleave(H // G, dim=1)                              # (b,H,N)
+    Ch = C.to(dtype).repeat_interleave(H // G, dim=1)
+    new_state = state.to(dtype) * dA + (dt[..., None] * Bh[:, :, None, :]) * x.to(dtype)[..., None]
+    out = (new_state * Ch[:, :, None, :]).sum(-1)
+    if D is not None:
+        out = out + x.to(dtype) * D.to(dtype)
+    if z is not None:
+        out = out * F.silu(z.to(dtype))
+    return out, new_state
+
+
+def mixer_decode_step_ref(p: dict, hidden_states: torch.Tensor, conv_state: torch.Tensor, ssm_state: torch.Tensor, *,
+                          num_heads: int, head_dim: int, n_groups: int, ssm_state_size: int, eps: float = 1e-5,
+                          time_step_limit: Sequence[float] = (0.0, float("inf")), dtype=torch.float32):
+    """One cached decode step of the mixer: hidden_states (b,1,hidden), conv_state (b,conv_dim,K), ssm_state
+    (b,H,P,N) -> (out (b,1,hidden), new conv_state, new ssm_state)."""
+    H, P, G, N = num_heads, head_dim, n_groups, ssm_state_size
+    d_inner, conv_dim = H * P, H * P + 2 * G * N
+    b = hidden_states.shape[0]
+    proj = F.linear(hidden_states.to(dtype), p["in_proj.weight"].to(dtype))[:, 0]         # :677
+    gate, xBC, dt = proj.split([d_inner, conv_dim, H], dim=-1)
+    xBC_c, conv_state = causal_conv1d_update_ref(xBC, conv_state, p["conv1d.weight"].squeeze(1),
+                                                 p.get("conv1d.bias"), "silu", dtype)      # :684-696
+    x, Bm, Cm = xBC_c.split([d_inner, G * N, G * N], dim=-1)
+    A = -torch.exp(p["A_log"].float())[:, None, None].expand(H, P, N)                      # :715, :727
+    dtv = dt[:, :, None].expand(b, H, P)
+    dtv = torch.clamp(F.softplus(dtv + p["dt_bias"].to(dtype)[:, None]), time_step_limit[0], time_step_limit[1])
+    y, ssm_state = selective_state_update_ref(ssm_state, x.reshape(b, H, P), dtv, A, Bm.reshape(b, G, N),
+                                              Cm.reshape(b, G, N), D=p["D"].to(dtype)[:, None].expand(H, P),
+                                              dtype=dtype)                                 # :720-768
+    yn = gated_rmsnorm_ref(y.reshape(b, 1, d_inner), p["norm.weight"], None, z=gate[:, None], eps=eps,
+                           group_size=d_inner // G, norm_before_gate=False, dtype=dtype)   # :853
+    return F.linear(yn, p["out_proj.weight"].to(dtype)), conv_state, ssm_state             # :858
+
+
+# --------------------------------------------------------------------------------------------
 # sequence sharding algebra (new work; SURVEY.md section 8e) -- used to check the multi-GPU path
 # --------------------------------------------------------------------------------------------
 def fold_boundary_states(local_states: Sequence[torch.Tensor], local_logdecay: Sequence[torch.Tensor],

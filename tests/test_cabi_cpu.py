@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert set(declared) == set(L.EXPORTS)
-    assert lib.tv_abi_version() == L.TV_ABI_VERSION == 2
+    assert lib.tv_abi_version() == L.TV_ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header_sizes():
@@ -39,6 +39,12 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(L.ConvParams) == 6 * 8 + 4 * 4 + 4 * 8 + 2 * 4
     assert ctypes.sizeof(L.RmsnormParams) == 5 * 8 + 8 + 2 * 4 + 3 * 8 + 3 * 4 + 4   # + tail padding
     assert ctypes.sizeof(L.SsdParams) == 12 * 8 + 7 * 4 + 4 + 15 * 8 + 2 * 4 + 2 * 4 + 4 * 4
+
+
+def test_decode_struct_layouts():
+    import timeviper_b200._lib as L
+    assert ctypes.sizeof(L.ConvUpdateParams) == 96      # sizeof(tv_conv1d_update_params), gcc x86-64
+    assert ctypes.sizeof(L.SsuParams) == 288            # sizeof(tv_ssu_params)
 
 
 def test_null_and_invalid_arguments_return_error_codes_without_touching_a_gpu():
@@ -83,9 +89,13 @@ def test_no_cpu_fallback():
                                               ssm_state_size=8, chunk_size=64))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 4, 32))
-    for fn in (tv.causal_conv1d_update, tv.selective_state_update, tv.mamba_split_conv1d_scan_combined):
-        with pytest.raises(NotImplementedError):
-            fn()
+    with pytest.raises(NotImplementedError):                       # training fwd+bwd is outside this path
+        tv.mamba_split_conv1d_scan_combined()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):      # the decode-step operators are CUDA-only too
+        tv.causal_conv1d_update(torch.zeros(1, 8), torch.zeros(1, 8, 4), torch.zeros(8, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tv.selective_state_update(torch.zeros(1, 2, 4, 8), torch.zeros(1, 2, 4), torch.zeros(1, 2, 4),
+                                  torch.zeros(2, 4, 8), torch.zeros(1, 1, 8), torch.zeros(1, 1, 8))
 
 
 def test_mixer_loads_reference_state_dict(golden_dir):

@@ -113,3 +113,20 @@ def test_conv_ref_matches_torch_conv1d_and_halo():
     o1, f1 = R.causal_conv1d_ref(x[..., :20], w, bias)
     o2, _ = R.causal_conv1d_ref(x[..., 20:], w, bias, initial_states=f1)
     assert torch.allclose(torch.cat([o1, o2], -1), out, atol=1e-6)
+
+
+@pytest.mark.parametrize("path", _cases(), ids=lambda p: os.path.basename(p)[6:-4])
+def test_decode_step_oracle_matches_reference_golden(path):
+    """Three cached single-token steps (torch_forward's cache_position > 0 branch, modeling_nano.py:683-696, 716-773)
+    continued from the reference's own prefill cache: outputs and both states after the last step."""
+    d, m = _load(path)
+    conv, ssm = d["conv_state"], d["ssm_state"]
+    outs = []
+    for i in range(d["decode_hidden_states"].shape[1]):
+        o, conv, ssm = R.mixer_decode_step_ref(
+            d, d["decode_hidden_states"][:, i:i + 1], conv, ssm, num_heads=m["H"], head_dim=m["P"], n_groups=m["G"],
+            ssm_state_size=m["N"], time_step_limit=tuple(d["time_step_limit"].tolist()))
+        outs.append(o)
+    assert relerr(torch.cat(outs, dim=1), d["decode_out"]) < 2e-5
+    assert relerr(ssm, d["decode_ssm_state"]) < 2e-5
+    assert torch.equal(conv, d["decode_conv_state"])

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("TV_LIB_PATH") or os.path.join(HERE, "libtimeviper_b20
 
 TV_F32, TV_BF16 = 0, 1
 TV_SSD_FULL, TV_SSD_STATE_ONLY, TV_SSD_DT_ONLY = 0, 1, 2
-TV_ABI_VERSION = 2
+TV_ABI_VERSION = 3
 TV_OK, TV_ERR_INVALID, TV_ERR_UNSUPPORTED, TV_ERR_CUDA, TV_ERR_WORKSPACE = 0, -1, -2, -3, -4
 
 
@@ -46,9 +46,35 @@ class SsdParams(C.Structure):
                 ("dtype", C.c_int32), ("mode", C.c_int32), ("force_simt", C.c_int32), ("reuse_dt_cumsum", C.c_int32)]
 
 
+class ConvUpdateParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("conv_state", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("out", C.c_void_p), ("batch", C.c_int32), ("dim", C.c_int32), ("width", C.c_int32),
+                ("state_len", C.c_int32), ("x_batch_stride", C.c_int64), ("out_batch_stride", C.c_int64),
+                ("state_batch_stride", C.c_int64), ("state_dim_stride", C.c_int64),
+                ("silu", C.c_int32), ("dtype", C.c_int32)]
+
+
+class SsuParams(C.Structure):
+    _fields_ = [("state", C.c_void_p), ("x", C.c_void_p), ("dt", C.c_void_p), ("A", C.c_void_p), ("B", C.c_void_p),
+                ("C", C.c_void_p), ("D", C.c_void_p), ("z", C.c_void_p), ("dt_bias", C.c_void_p), ("out", C.c_void_p),
+                ("batch", C.c_int32), ("nheads", C.c_int32), ("headdim", C.c_int32), ("ngroups", C.c_int32),
+                ("dstate", C.c_int32),
+                ("x_batch_stride", C.c_int64), ("x_head_stride", C.c_int64), ("x_dim_stride", C.c_int64),
+                ("dt_batch_stride", C.c_int64), ("dt_head_stride", C.c_int64), ("dt_dim_stride", C.c_int64),
+                ("a_head_stride", C.c_int64), ("a_dim_stride", C.c_int64), ("a_state_stride", C.c_int64),
+                ("b_batch_stride", C.c_int64), ("b_group_stride", C.c_int64),
+                ("c_batch_stride", C.c_int64), ("c_group_stride", C.c_int64),
+                ("d_head_stride", C.c_int64), ("d_dim_stride", C.c_int64),
+                ("z_batch_stride", C.c_int64), ("z_head_stride", C.c_int64), ("z_dim_stride", C.c_int64),
+                ("bias_head_stride", C.c_int64), ("bias_dim_stride", C.c_int64),
+                ("dt_softplus", C.c_int32), ("dt_min", C.c_float), ("dt_max", C.c_float),
+                ("dtype", C.c_int32), ("state_dtype", C.c_int32)]
+
+
 EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd",
            "tv_ssd_workspace_bytes", "tv_ssd_chunk_scan_fwd", "tv_ssd_kernel_family",
-           "tv_ssd_fold_boundary_states", "tv_debug_set_trace", "tv_debug_set_ablate")
+           "tv_ssd_fold_boundary_states", "tv_causal_conv1d_update", "tv_selective_state_update",
+           "tv_debug_set_trace", "tv_debug_set_ablate")
 
 _lib = None
 
@@ -78,6 +104,10 @@ def load():
                                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                                 C.c_void_p]
     lib.tv_ssd_fold_boundary_states.restype = C.c_int
+    lib.tv_causal_conv1d_update.argtypes = [C.POINTER(ConvUpdateParams), C.c_void_p]
+    lib.tv_causal_conv1d_update.restype = C.c_int
+    lib.tv_selective_state_update.argtypes = [C.POINTER(SsuParams), C.c_void_p]
+    lib.tv_selective_state_update.restype = C.c_int
     lib.tv_debug_set_trace.argtypes = [C.c_void_p]
     lib.tv_debug_set_trace.restype = None
     lib.tv_debug_set_ablate.argtypes = [C.c_int]

@@ -215,6 +215,29 @@ class Mamba2MixerPrefill(nn.Module):
             cache_params.update_ssm_state(layer_idx=self.layer_idx, new_ssm_state=ssm_state)
         return out_host
 
+    def decode_step(self, hidden_states, cache_params):
+        """One cached token (modeling_nano.py:484-546): hidden_states (b, 1, hidden) -> (b, 1, hidden); the conv state
+        (b, conv_dim, K) and the fp32 SSM state (b, H, P, N) in ``cache_params`` are updated in place by the kernels.
+        dt is clamped to ``time_step_limit`` as in prefill and in torch_forward (:725) -- the reference's fast decode
+        branch omits the clamp, which only differs for a non-default limit."""
+        b = hidden_states.shape[0]
+        if hidden_states.shape[1] != 1:
+            raise NotImplementedError("decode_step takes one new token per call")
+        H, P, G, N = self.num_heads, self.head_dim, self.n_groups, self.ssm_state_size
+        gts = G * N
+        projected = self.in_proj(hidden_states).squeeze(1)                      # :472, :489
+        gate, xBC, dt = projected.split([self.intermediate_size, self.conv_dim, H], dim=-1)
+        xBC = ops.causal_conv1d_update(xBC, cache_params.conv_states[self.layer_idx],          # :495-501
+                                       self.conv1d.weight.squeeze(1), self.conv1d.bias, self.activation)
+        x, B, C = torch.split(xBC, [self.intermediate_size, gts, gts], dim=-1)
+        A = self.decay_rates()[:, None, None].expand(H, P, N)                   # :514-519
+        y = ops.selective_state_update(                                         # :528-539
+            cache_params.ssm_states[self.layer_idx], x.view(b, H, P), dt[:, :, None].expand(b, H, P), A,
+            B.view(b, G, N), C.view(b, G, N), self.f32_param("D")[:, None].expand(H, P), z=None,
+            dt_bias=self.f32_param("dt_bias")[:, None].expand(H, P), dt_softplus=True, _dt_limit=self.time_step_limit)
+        y = self.norm(y.view(b, H * P), gate)                                   # :543
+        return self.out_proj(y)[:, None, ...]                                   # :546
+
     def forward(self, hidden_states, cache_params=None, cache_position=None, attention_mask=None, seq_idx=None):
         if not hidden_states.is_cuda:
             raise RuntimeError("Mamba2MixerPrefill runs on CUDA only: there is no CPU fallback "
@@ -222,7 +245,7 @@ class Mamba2MixerPrefill(nn.Module):
         if seq_idx is not None:
             raise NotImplementedError("seq_idx (packed training samples) is outside the prefill path")
         if cache_params is not None and cache_position is not None and cache_position[0] > 0:
-            raise NotImplementedError("single-token decode (modeling_nano.py:484-546) is outside the prefill path")
+            return self.decode_step(hidden_states, cache_params)
         if attention_mask is not None and attention_mask.shape[1] > 1 and attention_mask.shape[0] > 1:
             # apply_mask_to_padding_states, modeling_nano.py:189-201 (a no-op at batch 1)
             hidden_states = (hidden_states * attention_mask[:, :, None]).to(hidden_states.dtype)

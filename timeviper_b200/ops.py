@@ -18,6 +18,8 @@ import torch
 
 from . import _lib as L
 
+_byref = C.byref       # `C` is also the name of the SSM output-projection argument in the reference signatures
+
 _DT = {torch.float32: L.TV_F32, torch.bfloat16: L.TV_BF16}
 
 
@@ -297,15 +299,93 @@ def ssd_kernel_family(dtype, headdim, dstate, chunk_size, nheads=128, ngroups=8)
     return "tcgen05" if L.load().tv_ssd_kernel_family(C.byref(p)) == 1 else "simt"
 
 
-# -- names the reference's fast-path gate needs to be non-None (modeling_nano.py:89-97); decode and training
-#    are outside the prefill path, so they fail loudly instead of silently computing something else --------
-def causal_conv1d_update(*args, **kwargs):
-    raise NotImplementedError("causal_conv1d_update (single-token decode) is outside the prefill path")
+# ------------------------------------------------------------------------------------------------
+# single-token decode step (call sites modeling_nano.py:495-501, :528-539)
+def causal_conv1d_update(x, conv_state, weight, bias=None, activation=None, cache_seqlens=None, conv_state_indices=None):
+    """x: (batch, dim) [or (batch, dim, 1)]; conv_state: (batch, dim, state_len >= width), updated IN PLACE (shifted left
+    by one column, x appended); weight: (dim, width); bias: (dim,).  Returns out with the shape of x."""
+    if activation not in (None, "silu", "swish"):
+        raise NotImplementedError("activation must be None, silu, or swish")
+    if cache_seqlens is not None or conv_state_indices is not None:
+        raise NotImplementedError("causal_conv1d_update: circular-buffer / indexed states are outside this path")
+    _require_cuda(x, conv_state, weight, bias)
+    squeeze = x.dim() == 3
+    if squeeze:
+        if x.shape[-1] != 1:
+            raise NotImplementedError("causal_conv1d_update: one new token per call")
+        x = x.squeeze(-1)
+    b, dim = x.shape
+    width = weight.shape[1]
+    if conv_state.shape[:2] != (b, dim) or conv_state.shape[2] < width or conv_state.stride(2) != 1:
+        raise ValueError("causal_conv1d_update: conv_state must be (batch, dim, state_len >= width), unit last stride")
+    if conv_state.dtype != x.dtype:
+        raise ValueError("causal_conv1d_update: conv_state and x must have the same dtype")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    weight = weight.to(x.dtype).contiguous()
+    bias = None if bias is None else bias.to(x.dtype).contiguous()
+    out = torch.empty((b, dim), dtype=x.dtype, device=x.device)
+    p = L.ConvUpdateParams(x=_ptr(x), conv_state=_ptr(conv_state), weight=_ptr(weight), bias=_ptr(bias), out=_ptr(out),
+                           batch=b, dim=dim, width=width, state_len=conv_state.shape[2], x_batch_stride=x.stride(0),
+                           out_batch_stride=out.stride(0), state_batch_stride=conv_state.stride(0),
+                           state_dim_stride=conv_state.stride(1), silu=int(activation in ("silu", "swish")),
+                           dtype=_dtype_code(x, "causal_conv1d_update"))
+    L.check(L.load().tv_causal_conv1d_update(C.byref(p), _stream(x)), "causal_conv1d_update")
+    return out.unsqueeze(-1) if squeeze else out
 
 
-def selective_state_update(*args, **kwargs):
-    raise NotImplementedError("selective_state_update (single-token decode) is outside the prefill path")
+def selective_state_update(state, x, dt, A, B, C, D=None, z=None, dt_bias=None, dt_softplus=False,
+                           state_batch_indices=None, _dt_limit=(0.0, float("inf"))):
+    """state: (batch, nheads, headdim, dstate), updated IN PLACE; x, dt, z: (batch, nheads, headdim); A: (nheads,
+    headdim, dstate); B, C: (batch, ngroups, dstate); D, dt_bias: (nheads, headdim).  Expanded (stride-0) views are
+    taken as they are.  Returns out (batch, nheads, headdim)."""
+    if state_batch_indices is not None:
+        raise NotImplementedError("selective_state_update: indexed states are outside this path")
+    if state.dim() != 4 or x.dim() != 3:
+        raise NotImplementedError("selective_state_update: the multi-head form (state (b,H,P,N), x (b,H,P)) only")
+    _require_cuda(state, x, dt, A, B, C, D, z, dt_bias)
+    b, H, P, N = state.shape
+    G = B.shape[1]
+    assert x.shape == (b, H, P) and dt.shape == (b, H, P) and A.shape == (H, P, N)
+    assert B.shape == (b, G, N) and C.shape == (b, G, N) and H % G == 0
+    if D is not None:
+        assert D.shape == (H, P)
+    if z is not None:
+        assert z.shape == x.shape
+    if dt_bias is not None:
+        assert dt_bias.shape == (H, P)
+    if not state.is_contiguous():
+        raise ValueError("selective_state_update: state must be contiguous (it is updated in place)")
+    code = _dtype_code(x, "selective_state_update")
+    dt, B, C = dt.to(x.dtype), B.to(x.dtype), C.to(x.dtype)
+    if B.stride(-1) != 1:
+        B = B.contiguous()
+    if C.stride(-1) != 1:
+        C = C.contiguous()
+    z = None if z is None else z.to(x.dtype)
+    f32 = lambda t: None if t is None else (t if t.dtype == torch.float32 else t.float())   # noqa: E731
+    A32, D32, bias32 = f32(A), f32(D), f32(dt_bias)
+    out = torch.empty((b, H, P), dtype=x.dtype, device=x.device)
+    st3 = lambda t: (0, 0, 0) if t is None else tuple(t.stride())                            # noqa: E731
+    st2 = lambda t: (0, 0) if t is None else tuple(t.stride())                               # noqa: E731
+    lo, hi = float(_dt_limit[0]), float(_dt_limit[1])
+    p = L.SsuParams(state=_ptr(state), x=_ptr(x), dt=_ptr(dt), A=_ptr(A32), B=_ptr(B), C=_ptr(C), D=_ptr(D32), z=_ptr(z),
+                    dt_bias=_ptr(bias32), out=_ptr(out), batch=b, nheads=H, headdim=P, ngroups=G, dstate=N,
+                    x_batch_stride=x.stride(0), x_head_stride=x.stride(1), x_dim_stride=x.stride(2),
+                    dt_batch_stride=dt.stride(0), dt_head_stride=dt.stride(1), dt_dim_stride=dt.stride(2),
+                    a_head_stride=A32.stride(0), a_dim_stride=A32.stride(1), a_state_stride=A32.stride(2),
+                    b_batch_stride=B.stride(0), b_group_stride=B.stride(1),
+                    c_batch_stride=C.stride(0), c_group_stride=C.stride(1),
+                    d_head_stride=st2(D32)[0], d_dim_stride=st2(D32)[1],
+                    z_batch_stride=st3(z)[0], z_head_stride=st3(z)[1], z_dim_stride=st3(z)[2],
+                    bias_head_stride=st2(bias32)[0], bias_dim_stride=st2(bias32)[1],
+                    dt_softplus=int(bool(dt_softplus)), dt_min=lo, dt_max=hi if math.isfinite(hi) else float("inf"),
+                    dtype=code, state_dtype=_dtype_code(state, "selective_state_update(state)"))
+    L.check(L.load().tv_selective_state_update(_byref(p), _stream(x)), "selective_state_update")
+    return out
 
 
+# -- the remaining name the reference's fast-path gate needs to be non-None (modeling_nano.py:89-97): training is
+#    outside this path, so it fails loudly instead of silently computing something else -------------------------
 def mamba_split_conv1d_scan_combined(*args, **kwargs):
     raise NotImplementedError("mamba_split_conv1d_scan_combined (training fwd+bwd) is outside the prefill path")
