@@ -95,7 +95,8 @@ def test_mixer_decode_steps_against_reference_golden(tv, path):
             outs.append(mixer(hs[:, i:i + 1], cache_params=cache, cache_position=torch.tensor([L + i])))
     assert relerr(torch.cat(outs, dim=1), torch.from_numpy(z["decode_out"])) < 1e-4
     assert relerr(cache.ssm_states[0], torch.from_numpy(z["decode_ssm_state"])) < 1e-4
-    assert torch.equal(cache.conv_states[0].cpu(), torch.from_numpy(z["decode_conv_state"]))
+    # the new columns are in_proj outputs: cuBLAS vs CPU fp32 summation order, not bit-equal
+    assert relerr(cache.conv_states[0], torch.from_numpy(z["decode_conv_state"])) < 1e-5
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
@@ -126,4 +127,4 @@ def test_decode_continues_our_own_prefill(tv, dtype):
     assert step.shape == (1, 1, cfg.hidden_size)
     assert relerr(step, full[:, L:]) < tol
     assert relerr(cache.ssm_states[0], full_cache.ssm_states[0]) < tol
-    assert torch.equal(cache.conv_states[0], full_cache.conv_states[0])
+    assert relerr(cache.conv_states[0], full_cache.conv_states[0]) < 1e-5 + (tol if dtype == torch.bfloat16 else 0)

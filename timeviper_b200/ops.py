@@ -316,10 +316,15 @@ def causal_conv1d_update(x, conv_state, weight, bias=None, activation=None, cach
         x = x.squeeze(-1)
     b, dim = x.shape
     width = weight.shape[1]
-    if conv_state.shape[:2] != (b, dim) or conv_state.shape[2] < width or conv_state.stride(2) != 1:
-        raise ValueError("causal_conv1d_update: conv_state must be (batch, dim, state_len >= width), unit last stride")
+    if conv_state.shape[:2] != (b, dim) or conv_state.shape[2] < width:
+        raise ValueError("causal_conv1d_update: conv_state must be (batch, dim, state_len >= width)")
     if conv_state.dtype != x.dtype:
         raise ValueError("causal_conv1d_update: conv_state and x must have the same dtype")
+    if conv_state.stride(2) != 1:        # e.g. a channel-last state: update a dense copy, then write it back in place
+        dense = conv_state.contiguous()
+        out = causal_conv1d_update(x, dense, weight, bias, activation)
+        conv_state.copy_(dense)
+        return out.unsqueeze(-1) if squeeze else out
     if x.stride(1) != 1:
         x = x.contiguous()
     weight = weight.to(x.dtype).contiguous()
