@@ -82,5 +82,49 @@ def main():
               "conv", tuple(cache.conv_states[0].shape), "->", os.path.getsize(path) // 1024, "KiB")
 
 
+HYBRID_CASES = {
+    # name: (hidden, H, P, G, N, Q, attention heads, kv heads, attention head dim, MLP width, pattern, L)
+    "m_attn_m_mlp_ragged150": (64, 4, 16, 1, 32, 64, 4, 2, 16, 128, "M*M-", 150),
+    "9b_head_geometry_ragged300": (96, 4, 80, 1, 128, 128, 4, 2, 24, 160, "M-M*", 300),   # P=80, N=128, Q=128: tcgen05 path in bf16
+}
+
+
+def main_hybrid():
+    """The whole layer loop of the reference's NemotronHModel.forward (modeling_nano.py:1550-1746) on CPU.  The block body
+    enters ``torch.cuda.stream(torch.cuda.default_stream(dev))`` (:938); on this CPU-only box the harness replaces those
+    two torch functions with no-ops -- the reference stays unmodified."""
+    import contextlib
+    mn, Cfg = load_reference()
+    torch.cuda.default_stream = lambda device=None: None
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    out_dir = os.path.join(HERE, "..", "tests", "golden")
+    for name, (hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pattern, L) in HYBRID_CASES.items():
+        torch.manual_seed(4321)
+        cfg = Cfg(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, mamba_n_groups=G, ssm_state_size=N,
+                  mamba_chunk_size=Q, mamba_d_conv=4, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                  layer_norm_epsilon=1e-5, num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd,
+                  intermediate_size=mlp, vocab_size=100)
+        cfg._attn_implementation = "eager"
+        model = mn.NemotronHModel(cfg).float().eval()
+        with torch.no_grad():
+            for layer in model.layers:
+                if layer.block_type == "mamba":
+                    layer.mixer.A_log.copy_(torch.log(torch.rand(H) * 15 + 1))
+                    layer.mixer.dt_bias.copy_(torch.randn(H) * 0.5 - 2.0)
+                    layer.mixer.D.copy_(torch.randn(H))
+                layer.norm.weight.copy_(1.0 + 0.1 * torch.randn(hidden))
+            x = torch.randn(1, L, hidden)
+            out = model(inputs_embeds=x, use_cache=False)
+        hs = out[0] if isinstance(out, tuple) else out.last_hidden_state
+        blob = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+        blob.update(inputs_embeds=x.numpy(), last_hidden_state=hs.numpy(),
+                    dims=np.array([hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, L], dtype=np.int64),
+                    pattern=np.array(pattern))
+        path = os.path.join(out_dir, f"hybrid_{name}.npz")
+        np.savez_compressed(path, **blob)
+        print(name, "last_hidden_state", tuple(hs.shape), "->", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     main()
+    main_hybrid()

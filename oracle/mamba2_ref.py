@@ -299,6 +299,47 @@ def mixer_decode_step_ref(p: dict, hidden_states: torch.Tensor, conv_state: torc
 
 
 # --------------------------------------------------------------------------------------------
+# hybrid stack prefill: NemotronHModel layer loop, modeling_nano.py:1550-1746; block :906-967;
+# attention :1012-1117 (GQA, no rotary embedding, causal); MLP :970-996 (squared ReLU); RMSNorm :888-904
+# --------------------------------------------------------------------------------------------
+def rmsnorm_ref(x, weight, eps, dtype=torch.float32):
+    h = x.to(dtype)
+    return weight.to(dtype) * (h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + eps))
+
+
+def hybrid_forward_ref(p: dict, inputs_embeds: torch.Tensor, *, pattern: str, num_heads: int, head_dim: int,
+                       n_groups: int, ssm_state_size: int, chunk_size: int, attn_heads: int, kv_heads: int,
+                       attn_head_dim: int, eps: float = 1e-5, group_map: str = "kernel", dtype=torch.float32):
+    """p: a NemotronHModel state_dict (layers.N.norm.weight, layers.N.mixer.*, norm_f.weight).  Returns the last hidden
+    states (b, L, hidden) after norm_f."""
+    h = inputs_embeds.to(dtype)
+    b, L, _ = h.shape
+    for i, kind in enumerate(pattern):
+        pre = f"layers.{i}."
+        x = rmsnorm_ref(h, p[pre + "norm.weight"], eps, dtype)                                    # :941
+        sub = {k[len(pre) + 6:]: v for k, v in p.items() if k.startswith(pre + "mixer.")}
+        if kind == "M":
+            y, _, _ = mixer_forward_ref(sub, x, num_heads=num_heads, head_dim=head_dim, n_groups=n_groups,
+                                        ssm_state_size=ssm_state_size, chunk_size=chunk_size, eps=eps,
+                                        group_map=group_map, dtype=dtype)
+        elif kind == "*":
+            q = F.linear(x, sub["q_proj.weight"].to(dtype)).view(b, L, attn_heads, attn_head_dim).transpose(1, 2)
+            k = F.linear(x, sub["k_proj.weight"].to(dtype)).view(b, L, kv_heads, attn_head_dim).transpose(1, 2)
+            v = F.linear(x, sub["v_proj.weight"].to(dtype)).view(b, L, kv_heads, attn_head_dim).transpose(1, 2)
+            k = k.repeat_interleave(attn_heads // kv_heads, dim=1)                                 # repeat_kv :999-1009
+            v = v.repeat_interleave(attn_heads // kv_heads, dim=1)
+            att = (q @ k.transpose(-1, -2)) / (attn_head_dim ** 0.5)
+            att = att.masked_fill(torch.ones(L, L, dtype=torch.bool).triu(1), float("-inf")).softmax(-1)
+            y = F.linear((att @ v).transpose(1, 2).reshape(b, L, attn_heads * attn_head_dim), sub["o_proj.weight"].to(dtype))
+        elif kind == "-":
+            y = F.linear(torch.relu(F.linear(x, sub["up_proj.weight"].to(dtype))) ** 2, sub["down_proj.weight"].to(dtype))
+        else:
+            raise ValueError(kind)
+        h = h + y                                                                                  # :965
+    return rmsnorm_ref(h, p["norm_f.weight"], eps, dtype)                                          # :1715
+
+
+# --------------------------------------------------------------------------------------------
 # sequence sharding algebra (new work; SURVEY.md section 8e) -- used to check the multi-GPU path
 # --------------------------------------------------------------------------------------------
 def fold_boundary_states(local_states: Sequence[torch.Tensor], local_logdecay: Sequence[torch.Tensor],

@@ -1,0 +1,47 @@
+"""prefill of the hybrid stack (Mamba-2 layers on our kernels, attention via library SDPA, MLP via
+cuBLAS) against the reference's own NemotronHModel.forward (tests/golden/hybrid_*.npz, oracle/gen_golden.py) in fp32,
+and against the oracle in bf16.  `pytest -m gpu`."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mamba2_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _cases():
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "hybrid_*.npz")))
+
+
+@pytest.mark.parametrize("path", _cases(), ids=lambda p: os.path.basename(p)[7:-4])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_hybrid_prefill_against_reference_golden(path, dtype, tol):
+    import timeviper_b200 as tv
+    z = np.load(path)
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, L = [int(v) for v in z["dims"]]
+    pattern = str(z["pattern"])
+    cfg = tv.Mamba2Config(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, n_groups=G, ssm_state_size=N,
+                          chunk_size=Q, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                          num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd, intermediate_size_mlp=mlp,
+                          vocab_size=100)
+    model = tv.HybridPrefillStack(cfg)
+    sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("pattern", "dims", "inputs_embeds", "last_hidden_state")}
+    model.load_state_dict(sd, strict=True)                 # the reference NemotronHModel's own parameter names
+    model = model.to(dtype).cuda().eval()
+    x = torch.from_numpy(z["inputs_embeds"]).to(dtype).cuda()
+    out = model(inputs_embeds=x)
+    assert out.shape == (1, L, hidden)
+    # bf16: several layers of bf16 rounding on a normalised output -- compared with the fp32 reference result
+    assert relerr(out, torch.from_numpy(z["last_hidden_state"])) < tol
+    ref = R.hybrid_forward_ref(sd, torch.from_numpy(z["inputs_embeds"]), pattern=pattern, num_heads=H, head_dim=P,
+                               n_groups=G, ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd)
+    assert relerr(out, ref) < tol

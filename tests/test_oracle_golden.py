@@ -130,3 +130,19 @@ def test_decode_step_oracle_matches_reference_golden(path):
     assert relerr(torch.cat(outs, dim=1), d["decode_out"]) < 2e-5
     assert relerr(ssm, d["decode_ssm_state"]) < 2e-5
     assert torch.equal(conv, d["decode_conv_state"])
+
+
+def _hybrid_cases(golden_dir=os.path.join(os.path.dirname(__file__), "golden")):
+    return sorted(glob.glob(os.path.join(golden_dir, "hybrid_*.npz")))
+
+
+@pytest.mark.parametrize("path", _hybrid_cases(), ids=lambda p: os.path.basename(p)[7:-4])
+def test_hybrid_stack_oracle_matches_reference_golden(path):
+    """Layer loop of the reference's NemotronHModel.forward (Mamba-2 / attention / MLP blocks + norm_f), CPU golden."""
+    z = np.load(path)
+    d = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("pattern",)}
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, L = [int(v) for v in z["dims"]]
+    out = R.hybrid_forward_ref(d, d["inputs_embeds"], pattern=str(z["pattern"]), num_heads=H, head_dim=P, n_groups=G,
+                               ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd,
+                               group_map="torch_forward")
+    assert relerr(out, d["last_hidden_state"]) < 2e-5

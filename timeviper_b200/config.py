@@ -23,6 +23,17 @@ class Mamba2Config:
     use_bias: bool = False
     mamba_hidden_act: str = "silu"
     num_hidden_layers: int = 56
+    # the other two block types of the hybrid stack (timeviper_b200/hybrid.py; configuration_nano.py:137-175)
+    hybrid_override_pattern: str = "M"          # one character per layer: M = Mamba-2, * = attention, - = MLP
+    num_attention_heads: int = 40
+    num_key_value_heads: int = 8
+    head_dim: int = 128                         # attention head dim
+    attention_bias: bool = False
+    intermediate_size_mlp: int = 15680          # NemotronHConfig.intermediate_size (ours is d_inner of the mixer)
+    mlp_bias: bool = False
+    mlp_hidden_act: str = "relu2"
+    residual_in_fp32: bool = False
+    vocab_size: int = 131072
 
     @property
     def intermediate_size(self):
@@ -52,4 +63,7 @@ class Mamba2Config:
     def from_hf(cls, cfg):
         """From a reference NemotronHConfig (or anything with the same attributes)."""
         names = [f for f in cls.__dataclass_fields__]
-        return cls(**{n: getattr(cfg, n) for n in names if hasattr(cfg, n)})
+        kw = {n: getattr(cfg, n) for n in names if hasattr(cfg, n) and getattr(cfg, n) is not None}
+        if hasattr(cfg, "intermediate_size"):       # the reference's name for the MLP width
+            kw["intermediate_size_mlp"] = cfg.intermediate_size
+        return cls(**kw)

@@ -1,0 +1,108 @@
+"""Prefill of the hybrid NemotronH stack: the layer loop of ``NemotronHModel.forward``
+(timeviper/model/llm/llm_repo/nano/modeling_nano.py:1550-1746) with the Mamba-2 layers on this package's kernels.
+
+Block = pre-norm + mixer + residual (``NemotronHBlock``, :906-967); mixer by ``hybrid_override_pattern``:
+  M  ``Mamba2MixerPrefill``                                   (this package)
+  *  ``NemotronHAttention`` (:1012-1117): GQA, no rotary embedding, causal -> library SDPA
+  -  ``NemotronHMLP`` (:970-996): down(relu(up(x))^2)          -> cuBLAS
+Parameter names are the reference's (``embeddings``, ``layers.N.norm``, ``layers.N.mixer.*``, ``norm_f``), so a reference
+``NemotronHModel.state_dict()`` loads strictly.  Only the Mamba-2 mixer is new work; attention and MLP are library calls
+kept here so that a whole prefill can be checked against the reference (tests/golden/hybrid_*.npz) and timed.
+Deliberately NOT mirrored: the per-layer ``isnan().any()`` host sync (:1690) -- it serialises the GPU every layer."""
+import torch
+from torch import nn
+
+from .mixer import Mamba2MixerPrefill
+
+
+class RMSNorm(nn.Module):
+    """NemotronHRMSNorm (:888-904): fp32 statistics, fp32 weight multiply, cast back."""
+
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, hidden_states):
+        dtype = hidden_states.dtype
+        h = hidden_states.to(torch.float32)
+        h = h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
+        return (self.weight.to(torch.float32) * h).to(dtype)
+
+
+class Attention(nn.Module):
+    def __init__(self, config, layer_idx=None):
+        super().__init__()
+        self.layer_idx = layer_idx
+        self.num_heads, self.num_key_value_heads, self.head_dim = (config.num_attention_heads, config.num_key_value_heads,
+                                                                   config.head_dim)
+        h = config.hidden_size
+        self.q_proj = nn.Linear(h, self.num_heads * self.head_dim, bias=config.attention_bias)
+        self.k_proj = nn.Linear(h, self.num_key_value_heads * self.head_dim, bias=config.attention_bias)
+        self.v_proj = nn.Linear(h, self.num_key_value_heads * self.head_dim, bias=config.attention_bias)
+        self.o_proj = nn.Linear(self.num_heads * self.head_dim, h, bias=config.attention_bias)
+
+    def forward(self, hidden_states):
+        b, L, _ = hidden_states.shape
+        q = self.q_proj(hidden_states).view(b, L, self.num_heads, self.head_dim).transpose(1, 2)
+        k = self.k_proj(hidden_states).view(b, L, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+        v = self.v_proj(hidden_states).view(b, L, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+        o = nn.functional.scaled_dot_product_attention(q, k, v, is_causal=L > 1,            # :1087-1094
+                                                       enable_gqa=self.num_heads != self.num_key_value_heads)
+        return self.o_proj(o.transpose(1, 2).reshape(b, L, self.num_heads * self.head_dim))
+
+
+class MLP(nn.Module):
+    def __init__(self, config, layer_idx=None):
+        super().__init__()
+        if config.mlp_hidden_act != "relu2":
+            raise NotImplementedError("NemotronH uses the squared-ReLU MLP")
+        self.up_proj = nn.Linear(config.hidden_size, config.intermediate_size_mlp, bias=config.mlp_bias)
+        self.down_proj = nn.Linear(config.intermediate_size_mlp, config.hidden_size, bias=config.mlp_bias)
+
+    def forward(self, x):
+        return self.down_proj(torch.square(torch.relu(self.up_proj(x))))
+
+
+_KIND = {"M": "mamba", "*": "attention", "-": "mlp"}
+
+
+class HybridBlock(nn.Module):
+    def __init__(self, config, layer_idx):
+        super().__init__()
+        self.block_type = _KIND[config.hybrid_override_pattern[layer_idx]]
+        self.residual_in_fp32 = config.residual_in_fp32
+        self.norm = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
+        self.mixer = {"mamba": Mamba2MixerPrefill, "attention": Attention, "mlp": MLP}[self.block_type](config, layer_idx)
+
+    def forward(self, hidden_states, cache_params=None, cache_position=None):
+        residual = hidden_states.to(torch.float32) if self.residual_in_fp32 else hidden_states
+        h = self.norm(hidden_states.to(self.norm.weight.dtype))
+        if self.block_type == "mamba":
+            h = self.mixer(h, cache_params=cache_params, cache_position=cache_position)
+        else:
+            h = self.mixer(h)
+        return residual + h
+
+
+class HybridPrefillStack(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        if len(config.hybrid_override_pattern) != config.num_hidden_layers:
+            raise ValueError("hybrid_override_pattern needs one character per layer")
+        self.config = config
+        self.embeddings = nn.Embedding(config.vocab_size, config.hidden_size)
+        self.layers = nn.ModuleList([HybridBlock(config, i) for i in range(config.num_hidden_layers)])
+        self.norm_f = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None):
+        """Prefill: (b, L) token ids or (b, L, hidden) embeddings -> last hidden states (b, L, hidden) after ``norm_f``.
+        ``cache_params`` (reference cache interface) receives the conv / SSM states of every Mamba-2 layer."""
+        if (input_ids is None) == (inputs_embeds is None):
+            raise ValueError("exactly one of input_ids / inputs_embeds")
+        h = self.embeddings(input_ids) if inputs_embeds is None else inputs_embeds
+        pos = torch.arange(h.shape[1], device=h.device)
+        for layer in self.layers:
+            h = layer(h, cache_params=cache_params, cache_position=pos)
+        return self.norm_f(h)

@@ -68,7 +68,10 @@ def causal_conv1d_into(_out, x, weight, bias=None, seq_idx=None, initial_states=
     if weight.shape[0] != dim or weight.dim() != 2:
         raise ValueError(f"causal_conv1d_fn: weight {tuple(weight.shape)} does not match dim {dim}")
     width = weight.shape[1]
-    if x.stride(1) != 1:                       # upstream also accepts channel-first; make it channel-last
+    vec = 16 // x.element_size()               # the kernel moves 16-byte pieces of a channel-last row
+    if x.stride(1) != 1 or x.stride(2) % vec or x.stride(0) % vec or x.data_ptr() % 16:
+        # upstream also accepts channel-first; a view whose rows are not 16-byte aligned (e.g. a split of an in_proj
+        # output of odd width) is repacked as well
         x = x.transpose(1, 2).contiguous().transpose(1, 2)
     weight = weight.to(x.dtype).contiguous()
     bias = None if bias is None else bias.to(x.dtype).contiguous()
@@ -107,16 +110,17 @@ def rmsnorm_fn(x, weight, bias, z=None, eps=1e-6, group_size=None, norm_before_g
     _require_cuda(x, weight, bias, z)
     shape = x.shape
     d = shape[-1]
-    x2 = x.reshape(-1, d)
-    if x2.stride(-1) != 1:
-        x2 = x2.contiguous()
+    vec = 16 // x.element_size()               # the kernel moves 16-byte pieces of a row
+
+    def aligned(t):                            # unit stride along d, 16-byte aligned rows; otherwise repack
+        return t if (t.stride(-1) == 1 and t.stride(0) % vec == 0 and t.data_ptr() % 16 == 0) else t.contiguous()
+
+    x2 = aligned(x.reshape(-1, d))
     z2 = None
     if z is not None:
         if z.shape != shape:
             raise ValueError("rmsnorm_fn: z must have the shape of x")
-        z2 = z.to(x.dtype).reshape(-1, d)
-        if z2.stride(-1) != 1:
-            z2 = z2.contiguous()
+        z2 = aligned(z.to(x.dtype).reshape(-1, d))
     if weight.shape != (d,):
         raise ValueError("rmsnorm_fn: weight must be (d,)")
     weight = weight.to(x.dtype).contiguous()
