@@ -165,3 +165,28 @@ def test_streamed_prefill_segment_schedule():
         assert max(sizes) <= seg + 127
     b = M._segment_bounds(131072, 16384, 128)
     assert b[1] == 2048 and b[-1] - b[-2] == 2048
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/timeviper"), reason="reference tree only exists in the build container")
+def test_hybrid_stack_mirrors_the_reference_model_parameters():
+    """HybridPrefillStack built from the reference's own NemotronHConfig has exactly the parameter names and shapes of
+    the reference NemotronHModel, so its state_dict loads strictly (timeviper_b200/hybrid.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_shim"))
+    sys.path.insert(0, "/root/reference/timeviper/model/llm/llm_repo")
+    import nano.modeling_nano as mn
+    from nano.configuration_nano import NemotronHConfig
+    import timeviper_b200 as tv
+    rcfg = NemotronHConfig(hidden_size=64, mamba_num_heads=4, mamba_head_dim=16, mamba_n_groups=2, ssm_state_size=32,
+                           mamba_chunk_size=64, mamba_d_conv=4, num_hidden_layers=5, hybrid_override_pattern="M*-M-",
+                           num_attention_heads=4, num_key_value_heads=2, head_dim=16, intermediate_size=96, vocab_size=50)
+    rcfg._attn_implementation = "eager"
+    ref = mn.NemotronHModel(rcfg)
+    cfg = tv.Mamba2Config.from_hf(rcfg)
+    assert (cfg.n_groups, cfg.chunk_size, cfg.intermediate_size_mlp, cfg.hybrid_override_pattern) == (2, 64, 96, "M*-M-")
+    ours = tv.HybridPrefillStack(cfg)
+    ref_sd, our_sd = ref.state_dict(), ours.state_dict()
+    assert set(ref_sd) == set(our_sd)
+    assert all(ref_sd[k].shape == our_sd[k].shape for k in ref_sd)
+    missing, unexpected = ours.load_state_dict(ref_sd, strict=True)
+    assert not missing and not unexpected
