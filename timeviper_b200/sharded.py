@@ -137,3 +137,60 @@ def sharded_mixer_forward(mixer, hidden_states_shard, group=None, cache_params=N
     projected = mixer.in_proj(hidden_states_shard)
     y, _ = sharded_scan_core(mixer, projected, group=group, cache_params=cache_params, ops=ops)
     return mixer.out_proj(y)
+
+
+class _HostPipe:
+    """Per-device double buffers, copy streams and events of ``sharded_prefill_from_host``."""
+
+    def __init__(self, dev, in_shape, out_shape, dtype):
+        self.key = (tuple(in_shape), tuple(out_shape), dtype)
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.d_in = [torch.empty(in_shape, dtype=dtype, device=dev) for _ in range(2)]
+        self.y = [None, None]                       # keeps the output of slot i alive until its D2H copy has run
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_compute = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.step = 0
+
+
+_host_pipes = {}
+
+
+@torch.no_grad()
+def sharded_prefill_from_host(mixer, hidden_host_shard, out_host_shard=None, group=None, cache_params=None):
+    """This rank's shard from (pinned) HOST memory to (pinned) host memory.  The H2D copy, the sharded mixer and the D2H
+    copy run on three streams with double-buffered device tensors, so when shards arrive back to back (one call per
+    sequence) the H2D copy of the next call overlaps the D2H copy of the previous one -- the two PCIe directions are
+    independent, and within ONE sequence they cannot overlap because every output depends on every earlier token.
+    The call returns once the work is enqueued; ``torch.cuda.synchronize()`` (or the returned event) before reading
+    ``out_host_shard``.  Returns (out_host_shard, done_event)."""
+    dev = mixer.in_proj.weight.device
+    b, L, _ = hidden_host_shard.shape
+    out_shape = (b, L, mixer.hidden_size)
+    if out_host_shard is None:
+        out_host_shard = torch.empty(out_shape, dtype=hidden_host_shard.dtype).pin_memory()
+    pipe = _host_pipes.get(dev.index)
+    if pipe is None or pipe.key != (tuple(hidden_host_shard.shape), out_shape, hidden_host_shard.dtype):
+        torch.cuda.synchronize(dev)
+        pipe = _host_pipes[dev.index] = _HostPipe(dev, hidden_host_shard.shape, out_shape, hidden_host_shard.dtype)
+    i = pipe.step % 2
+    first_use = pipe.step < 2
+    pipe.step += 1
+    cur = torch.cuda.current_stream(dev)
+    with torch.cuda.stream(pipe.s_in):
+        if not first_use:
+            pipe.s_in.wait_event(pipe.ev_compute[i])          # the mixer of two calls ago has read this input buffer
+        else:
+            pipe.s_in.wait_stream(cur)
+        pipe.d_in[i].copy_(hidden_host_shard, non_blocking=True)
+        pipe.ev_in[i].record(pipe.s_in)
+    cur.wait_event(pipe.ev_in[i])
+    y = sharded_mixer_forward(mixer, pipe.d_in[i], group=group, cache_params=cache_params)
+    pipe.ev_compute[i].record(cur)
+    with torch.cuda.stream(pipe.s_out):
+        pipe.s_out.wait_event(pipe.ev_compute[i])
+        out_host_shard.copy_(y, non_blocking=True)
+        pipe.ev_out[i].record(pipe.s_out)
+    y.record_stream(pipe.s_out)
+    pipe.y[i] = y
+    return out_host_shard, pipe.ev_out[i]
