@@ -87,7 +87,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,L", [(2, 128), (4, 256), (2, 70)])
+@pytest.mark.parametrize("world,L", [(2, 128), (4, 256), (2, 70), (8, 512)])
 def test_sharded_equals_unsharded_gloo(world, L):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
