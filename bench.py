@@ -178,9 +178,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist_on = world > 1
     if dist_on:
-        # The one collective on the critical path is a 5.24 MB/rank all-gather: NCCL's LL128 protocol is ~20 % faster
-        # than its default choice at that size (49 vs 62 us at 4 ranks, tools/ag_sweep.sh); a user setting wins.
-        os.environ.setdefault("NCCL_PROTO", "LL128")
+        # The one collective on the critical path is a 5.24 MB/rank all-gather: at 4 ranks NCCL's LL128 protocol is ~20 %
+        # faster than its default choice at that size (49 vs 62 us, tools/ag_sweep.sh).  Not measured in isolation at 8
+        # ranks (in-step 113 us with LL128 vs 95-105 us with the default in an earlier run), so NCCL keeps its own choice
+        # there; a user setting always wins.
+        if world <= 4:
+            os.environ.setdefault("NCCL_PROTO", "LL128")
         # high-priority NCCL stream: the halo all-gather overlaps the shard-wide conv instead of queueing behind it
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
