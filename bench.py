@@ -35,9 +35,25 @@ METRIC = "mamba2_mixer_prefill_tokens_per_s"
 UNIT = "tokens/s"
 # algorithmic bytes per token (SURVEY.md 8d / DESIGN.md), bf16, 9B dims
 BYTES_PER_TOKEN = {"conv1d": 49152, "ssd": 45312, "gated_rmsnorm": 61440}
-# per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from one `ncu --set full` capture of this
-# command at seqlen 131072 on 1 GPU (profiles/r01_summary.md); null for any other configuration
-NCU_TRAFFIC_128K = {"conv1d": 6.500e9, "ssd": 6.031e9 + 0.111e9, "gated_rmsnorm": 8.028e9}   # ssd = fused + dt/cumsum
+# Nanov2-9B Mamba-2 layer dims (timeviper_b200.config.Mamba2Config.nanov2_9b holds the same numbers --
+# repeated here so that the CPU reference arm never imports the product package, i.e. never maps its .so)
+DIMS_9B = dict(hidden=4480, H=128, P=80, G=8, N=128, Q=128, K=4)
+DIMS_9B["conv_dim"] = DIMS_9B["H"] * DIMS_9B["P"] + 2 * DIMS_9B["G"] * DIMS_9B["N"]
+DIMS_9B["proj"] = DIMS_9B["H"] * DIMS_9B["P"] + DIMS_9B["conv_dim"] + DIMS_9B["H"]
+
+
+def ncu_traffic(seqlen, world):
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the path kernels from the newest
+    profiles/rNN_ncu_traffic.json, which tools/ncu_traffic.py regenerates from an `ncu --set full` capture of this
+    command; None when no capture matches the configuration."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    if d.get("seqlen") != seqlen or d.get("n_gpus") != world:
+        return None, os.path.relpath(files[-1], ROOT)
+    return d["traffic_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
 
 
 def peaks():
@@ -97,20 +113,19 @@ def cpu_reference_tokens_per_s(sample_tokens, steps=1, warmup=0):
     """Reference CPU path (oracle port of torch_forward, kernel group mapping) on the host cores:
     conv -> SSD -> gated norm from a resident projected input, 9B dims, fp32."""
     from oracle import mamba2_ref as R
-    from timeviper_b200.config import Mamba2Config
-    cfg = Mamba2Config.nanov2_9b()
-    H, P, G, N = cfg.mamba_num_heads, cfg.mamba_head_dim, cfg.n_groups, cfg.ssm_state_size
+    d = DIMS_9B
+    H, P, G, N = d["H"], d["P"], d["G"], d["N"]
     torch.manual_seed(1234)
-    p = R.nemotron_random_params(cfg.hidden_size, H, P, G, N, nondegenerate=False)
+    p = R.nemotron_random_params(d["hidden"], H, P, G, N, nondegenerate=False)
     L = sample_tokens
-    proj = torch.randn(1, L, cfg.projection_size) * 0.5
+    proj = torch.randn(1, L, d["proj"]) * 0.5
 
     def step():
-        gate, xBC, dt = proj.split([H * P, cfg.conv_dim, H], dim=-1)
+        gate, xBC, dt = proj.split([H * P, d["conv_dim"], H], dim=-1)
         xc, _ = R.causal_conv1d_ref(xBC.transpose(1, 2), p["conv1d.weight"].squeeze(1), p["conv1d.bias"])
         x, Bm, Cm = xc.transpose(1, 2).split([H * P, G * N, G * N], dim=-1)
         y, s = R.ssd_chunked_ref(x.reshape(1, L, H, P), dt, -torch.exp(p["A_log"]), Bm.reshape(1, L, G, N),
-                                 Cm.reshape(1, L, G, N), cfg.chunk_size, D=p["D"], dt_bias=p["dt_bias"],
+                                 Cm.reshape(1, L, G, N), d["Q"], D=p["D"], dt_bias=p["dt_bias"],
                                  dt_softplus=True)
         return R.gated_rmsnorm_ref(y.reshape(1, L, H * P), p["norm.weight"], None, gate, 1e-5, H * P // G, False)
 
@@ -124,11 +139,49 @@ def cpu_reference_tokens_per_s(sample_tokens, steps=1, warmup=0):
     return L / dt_s, dt_s
 
 
+def cpu_threads(args):
+    """All host cores for the CPU arm: torchrun exports OMP_NUM_THREADS=1, which would otherwise make the arm run on a
+    single thread at N > 1 (the round-1 ratios at N = 2/4/8 were void for that reason)."""
+    n = args.cpu_threads or os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def reference_config1():
+    """BASELINE.json configs[0]: the LITERAL reference -- the unmodified NemotronHMamba2Mixer.forward -> torch_forward
+    (modeling_nano.py:671-859) -- small config (hidden 512, 16 heads x 80, G=1, N=128, Q=128), batch 1, 4096 tokens, fp32,
+    on the host cores.  Needs the reference package staged under baseline/_ref (oracle/stage_reference.py)."""
+    try:
+        from oracle import stage_reference
+        if not stage_reference.available():
+            return {"unavailable": "baseline/_ref/nano not staged on this box"}
+        mn, Cfg = stage_reference.load()
+        torch.manual_seed(1234)
+        hidden, H, P, G, N, Q, L = 512, 16, 80, 1, 128, 128, 4096
+        cfg = Cfg(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, mamba_n_groups=G, ssm_state_size=N,
+                  mamba_chunk_size=Q, mamba_d_conv=4, num_hidden_layers=2, hybrid_override_pattern="M-",
+                  layer_norm_epsilon=1e-5)
+        mixer = mn.NemotronHMamba2Mixer(cfg, layer_idx=0).float().eval()
+        hs = torch.randn(1, L, hidden)
+        best = None
+        with torch.no_grad():
+            for _ in range(2):
+                t0 = time.perf_counter()
+                mixer(hs)
+                dt_s = time.perf_counter() - t0
+                best = dt_s if best is None else min(best, dt_s)
+        return {"value": L / best, "unit": UNIT, "seconds": best, "kind": "_ref", "cores": torch.get_num_threads(),
+                "workload": "unmodified NemotronHMamba2Mixer.torch_forward, hidden 512, H16 P80 G1 N128 Q128, L=4096, fp32 "
+                            "(in_proj and out_proj included)"}
+    except Exception as e:      # never let the optional leg take the arm down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = cpu_threads(args)
     sample = args.cpu_sample
     tps, sec = cpu_reference_tokens_per_s(sample, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {
@@ -142,6 +195,9 @@ def run_reference(args):
                                    f"restatement), {cores} torch threads, os.cpu_count()={os.cpu_count()}"},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "same_config_note": "the literal torch_forward needs ~34 GB at the 9B dims (it materialises (b,c,l,s,h,n)); this arm "
+                            "times its memory-lean restatement on a bounded token sample of the same layer",
+        "config1_literal_reference": reference_config1(),
     }
     print(json.dumps(line), flush=True)
 
@@ -166,6 +222,41 @@ def time_region(fn, steps, dist_on):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return ms / steps
+
+
+def sharded_parity(tv, mixer, proj, rank, world):
+    """Self-validation of the sharded path at the timed configuration: rank 0 gathers every rank's projected shard, runs
+    the UNSHARDED core on the whole sequence once and compares (a) a strided token sample of every shard's output and
+    (b) the last rank's final SSM state with what the sharded run produced.  Relative errors = max|a-b| / max|b|."""
+    import torch.distributed as dist
+    dev = proj.device
+    with torch.no_grad():
+        y_sh, ssm_sh = tv.sharded_scan_core(mixer, proj)
+        stride = 257
+        sample = y_sh[:, ::stride].contiguous()
+        shards = [torch.empty_like(proj) for _ in range(world)] if rank == 0 else None
+        dist.gather(proj.contiguous(), shards, dst=0)
+        samples = [torch.empty_like(sample) for _ in range(world)] if rank == 0 else None
+        dist.gather(sample, samples, dst=0)
+        ssm_last = ssm_sh.clone()
+        dist.broadcast(ssm_last, src=world - 1)
+        res = torch.zeros(2, device=dev, dtype=torch.float64)
+        if rank == 0:
+            full = torch.cat(shards, dim=1)
+            del shards
+            y_full, ssm_full = mixer.scan_core(full, return_states=True)
+            Ls = proj.shape[1]
+            scale = float(y_full.float().abs().max())
+            y_err = 0.0
+            for r in range(world):
+                ref = y_full[:, r * Ls:(r + 1) * Ls][:, ::stride].float()
+                y_err = max(y_err, float((samples[r].float() - ref).abs().max()) / scale)
+            s_err = float((ssm_last - ssm_full).abs().max() / ssm_full.abs().max())
+            res[0], res[1] = y_err, s_err
+            del full, y_full
+        dist.broadcast(res, src=0)
+        torch.cuda.empty_cache()
+    return float(res[0]), float(res[1])
 
 
 def run_ours(args):
@@ -212,11 +303,29 @@ def run_ours(args):
         proj = mixer.in_proj(hs_dev)                                    # resident input of the hot path
     family = tv.ssd_kernel_family(torch.bfloat16, cfg.mamba_head_dim, cfg.ssm_state_size, cfg.chunk_size)
 
+    use_graph = not dist_on and not args.no_graph
+
     def core():
         with torch.no_grad():
             if dist_on:
                 return tv.sharded_scan_core(mixer, proj)[0]
+            if use_graph:       # the three kernels + the dt/cumsum pre-kernel replayed as ONE CUDA graph launch
+                return mixer.scan_core_graph(proj)
             return mixer.scan_core(proj)
+
+    parity = None
+    if dist_on:
+        y_rel, state_rel = sharded_parity(tv, mixer, proj, rank, world)
+        parity = {"y_rel": y_rel, "state_rel": state_rel, "tol": 2e-2,
+                  "what": "sharded vs one unsharded run on rank 0: strided token sample (every 257th) of every shard's "
+                          "output, and the last rank's final SSM state; bf16"}
+        if not (y_rel < 2e-2 and state_rel < 2e-2):
+            raise SystemExit(f"bench.py: sharded result out of tolerance: {parity}")
+    # kernels of libtimeviper_b200.so per step on this rank: counted by the library itself around one eager step
+    with torch.no_grad():
+        n0 = tv.launch_count()
+        (tv.sharded_scan_core(mixer, proj) if dist_on else mixer.scan_core(proj))
+        launches_per_step = tv.launch_count() - n0
 
     def e2e():
         with torch.no_grad():
@@ -272,6 +381,13 @@ def run_ours(args):
         e2e()
     ms_e2e = time_region(e2e, e2e_steps, dist_on)
 
+    # sustained: the same step back to back for a few seconds (the board settles into its power cap); reported beside
+    # the burst figure the headline `value` is
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / max(ms, 1e-3)))
+        ms_sus = time_region(core, n_sus, dist_on)
+        sustained = {"ms_per_step": ms_sus, "value": Ltot / (ms_sus * 1e-3), "unit": UNIT, "steps": n_sus}
     if dist_on:
         dist.barrier()
 
@@ -285,15 +401,12 @@ def run_ours(args):
         cpu_tps, cpu_sec = (None, None)
         cpu_block = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = torch.get_num_threads()
+            cores = cpu_threads(args)
             cpu_tps, cpu_sec = cpu_reference_tokens_per_s(args.cpu_sample)
             cpu_block = {"value": cpu_tps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.cpu_sample} tokens of the same layer, oracle/mamba2_ref.py (restatement of "
                                    f"the reference torch_forward), fp32, {cores} torch threads, {cpu_sec:.1f} s"}
-        # kernels of libtimeviper_b200.so per step on rank 0.  single GPU: conv, dt cumsum, fused SSD (5 stage kernels
-        # in the CUDA-core family), norm.  sharded: + suffix scan and state pass of pass 1 (the cumsum is shared by both
-        # passes); ranks > 0 add the 3-row halo conv and the boundary-state fold.
-        launches_per_step = {"simt": 7, "tcgen05": 4}[family] + (2 if dist_on else 0)
+        traffic, traffic_src = ncu_traffic(Ltot, world)
         line = {
             "metric": METRIC, "value": Ltot / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -312,8 +425,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / pk["hbm_gbs"],
-                         "traffic": NCU_TRAFFIC_128K[dom] if (Ltot == 131072 and world == 1) else None,
-                         "traffic_source": "profiles/r01_summary.md (ncu --set full, per launch, bytes)", "peak_source": pk["source"],
+                         "traffic": (traffic or {}).get(dom),
+                         "traffic_source": traffic_src, "peak_source": pk["source"],
                          "algorithmic_bytes_per_token": BYTES_PER_TOKEN[dom]},
             "kernels": kernels,
             "path_roofline": {"bytes_per_token": path_bytes,
@@ -321,6 +434,12 @@ def run_ours(args):
         }
         if cpu_block is not None:
             line["cpu_baseline"] = cpu_block
+        if parity is not None:
+            line["parity"] = parity
+        if sustained is not None:
+            line["sustained"] = sustained
+        line["config"]["launch"] = ("one CUDA graph replay per step (conv, dt/cumsum, fused SSD, norm)" if use_graph
+                                    else "eager kernel launches")
         print(json.dumps(line), flush=True)
     if dist_on:
         dist.destroy_process_group()
@@ -337,6 +456,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-segment", type=int, default=16384, help="tokens per streamed segment in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (default: all host cores)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="back-to-back seconds for the sustained step time")
+    ap.add_argument("--no-graph", action="store_true", help="N=1: launch the three kernels eagerly instead of one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,7 +94,8 @@ int tv_gated_rmsnorm_fwd(const tv_rmsnorm_params* p, void* stream);
  * chunk_logdecay_sum (the shard summary of the sequence-sharded path) and touches neither out, C, D nor z.
  * TV_SSD_DT_ONLY runs only the dt activation + per-chunk cumsum into `workspace` (it reads dt, A, dt_bias and no
  * other tensor -- x/B are only inspected for the family choice), so that a caller can overlap it with the conv
- * that produces x/B/C and pass reuse_dt_cumsum = 1 to the calls that follow.
+ * that produces x/B/C and pass reuse_dt_cumsum = 1 to the calls that follow.  The library remembers which dt tensor,
+ * dims, strides and limits each workspace was filled from and returns TV_ERR_INVALID for a reuse that does not match.
  * ------------------------------------------------------------------------------------------- */
 typedef enum { TV_SSD_FULL = 0, TV_SSD_STATE_ONLY = 1, TV_SSD_DT_ONLY = 2 } tv_ssd_mode;
 
@@ -197,6 +198,9 @@ void tv_debug_set_trace(void* device_buffer);
 /* Profiling builds only (python -m timeviper_b200.build --trace): bitmask of per-role work the fused SSD kernel skips,
  * to find the critical path by ablation (results are then wrong by construction).  No effect in normal builds. */
 void tv_debug_set_ablate(int mask);
+/* Number of kernels this library has enqueued so far in this process (all entry points, all streams): what bench.py
+ * reports as gpu_launches. */
+unsigned long long tv_debug_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -125,6 +125,43 @@ def main_hybrid():
         print(name, "last_hidden_state", tuple(hs.shape), "->", os.path.getsize(path) // 1024, "KiB")
 
 
+def main_masked():
+    """Batch 2, left-padded, with attention_mask: the reference multiplies the padded rows by zero before in_proj (:676)
+    and again after the conv (:707; fast path :471 and :625-627), so that silu(conv bias) of a padded position never
+    reaches x, B, C."""
+    mn, Cfg = load_reference()
+    out_dir = os.path.join(HERE, "..", "tests", "golden")
+    hidden, H, P, G, N, Q, L = 96, 4, 80, 1, 128, 128, 200
+    torch.manual_seed(2468)
+    cfg = Cfg(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, mamba_n_groups=G, ssm_state_size=N,
+              mamba_chunk_size=Q, mamba_d_conv=4, num_hidden_layers=2, hybrid_override_pattern="M-",
+              layer_norm_epsilon=1e-5)
+    mixer = mn.NemotronHMamba2Mixer(cfg, layer_idx=0).float().eval()
+    with torch.no_grad():
+        mixer.A_log.copy_(torch.log(torch.rand(H) * 15 + 1))
+        mixer.dt_bias.copy_(torch.randn(H) * 0.5 - 2.0)
+        mixer.D.copy_(torch.randn(H))
+        mixer.conv1d.bias.copy_(torch.randn(mixer.conv1d.bias.shape) * 0.5)      # a bias that matters at padded rows
+    hs = torch.randn(2, L, hidden)
+    mask = torch.ones(2, L)
+    mask[0, :37] = 0                                   # sequence 0: 37 pad tokens on the left; sequence 1: none
+    cache = mn.HybridMambaAttentionDynamicCache(cfg, batch_size=2, dtype=torch.float32)
+    with torch.no_grad():
+        out = mixer(hs, cache_params=cache, cache_position=torch.arange(L), attention_mask=mask)
+    blob = {k: v.detach().numpy() for k, v in mixer.state_dict().items()}
+    blob.update(hidden_states=hs.numpy(), attention_mask=mask.numpy(), out=out.numpy(),
+                conv_state=cache.conv_states[0].numpy(), ssm_state=cache.ssm_states[0].numpy(),
+                dims=np.array([hidden, H, P, G, N, Q, L], dtype=np.int64),
+                time_step_limit=np.array((0.0, float("inf")), dtype=np.float64))
+    path = os.path.join(out_dir, "masked_g1_batch2_leftpad37.npz")
+    np.savez_compressed(path, **blob)
+    print("masked batch 2:", tuple(out.shape), "->", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
-    main_hybrid()
+    if "--masked-only" in sys.argv:
+        main_masked()
+    else:
+        main()
+        main_hybrid()
+        main_masked()

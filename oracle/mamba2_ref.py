@@ -198,7 +198,7 @@ def gated_rmsnorm_ref(x, weight, bias=None, z=None, eps=1e-6, group_size=None, n
 def mixer_forward_ref(p: dict, hidden_states: torch.Tensor, *, num_heads: int, head_dim: int,
                       n_groups: int, ssm_state_size: int, chunk_size: int, conv_kernel: int = 4,
                       eps: float = 1e-5, time_step_limit: Sequence[float] = (0.0, float("inf")),
-                      group_map: str = "kernel", dtype=torch.float32, round_to=None):
+                      group_map: str = "kernel", dtype=torch.float32, round_to=None, attention_mask=None):
     """p: in_proj.weight (W,hidden), conv1d.weight (conv_dim,1,K), conv1d.bias, dt_bias, A_log, D,
     norm.weight, out_proj.weight.  Returns (out (b,L,hidden), conv_state (b,conv_dim,K), ssm_state (b,H,P,N)).
 
@@ -210,12 +210,18 @@ def mixer_forward_ref(p: dict, hidden_states: torch.Tensor, *, num_heads: int, h
     d_inner = H * P
     conv_dim = d_inner + 2 * G * N
     b, L, _ = hidden_states.shape
+    # apply_mask_to_padding_states (:189-201): only for batch > 1 and L > 1; before in_proj (:676) and after the conv (:707)
+    masked = attention_mask is not None and attention_mask.shape[0] > 1 and attention_mask.shape[1] > 1
+    if masked:
+        hidden_states = hidden_states.to(dtype) * attention_mask[:, :, None].to(dtype)
     proj = rnd(F.linear(hidden_states.to(dtype), p["in_proj.weight"].to(dtype)))          # :677
     gate, xBC, dt = proj.split([d_inner, conv_dim, H], dim=-1)                            # :679-681
     conv_state = conv_cache_state_ref(xBC, conv_kernel)                                    # :698-703
     xBC_c, _ = causal_conv1d_ref(xBC.transpose(1, 2), p["conv1d.weight"].squeeze(1),
                                  p.get("conv1d.bias"), activation="silu", dtype=dtype)    # :705
     xBC_c = rnd(xBC_c.transpose(1, 2))
+    if masked:
+        xBC_c = xBC_c * attention_mask[:, :, None].to(dtype)                              # :707
     x, Bm, Cm = xBC_c.split([d_inner, G * N, G * N], dim=-1)                               # :708-712
     A = -torch.exp(p["A_log"].float())                                                     # :715
     y, ssm_state = ssd_chunked_ref(x.reshape(b, L, H, P), dt, A, Bm.reshape(b, L, G, N),

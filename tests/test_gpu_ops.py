@@ -333,3 +333,26 @@ def test_streamed_prefill_from_host_equals_forward(tv):
     assert relerr(out, ref) < 2e-2
     assert relerr(c2.ssm, c1.ssm) < 2e-2
     assert torch.equal(c2.conv, c1.conv)
+
+
+def test_mixer_padding_mask_batch2_against_reference_golden(tv):
+    """Batch 2, left-padded, attention_mask: padded rows are zeroed before in_proj AND after the conv (reference fast path
+    modeling_nano.py:471, :625-627); golden vector from the reference's own forward."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "masked_g1_batch2_leftpad37.npz"))
+    hidden, H, P, G, N, Q, L = [int(v) for v in z["dims"]]
+    cfg = tv.Mamba2Config(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, n_groups=G, ssm_state_size=N, chunk_size=Q)
+    keys = ["in_proj.weight", "conv1d.weight", "conv1d.bias", "dt_bias", "A_log", "D", "norm.weight", "out_proj.weight"]
+    mixer = tv.Mamba2MixerPrefill(cfg).cuda()
+    mixer.load_state_dict({k: torch.from_numpy(z[k]) for k in keys}, strict=True)
+
+    class Cache:
+        conv_kernel_size = 4
+        def update_conv_state(self, layer_idx, new_conv_state, cache_init=False): self.conv = new_conv_state
+        def update_ssm_state(self, layer_idx, new_ssm_state): self.ssm = new_ssm_state
+    cache = Cache()
+    with torch.no_grad():
+        out = mixer(torch.from_numpy(z["hidden_states"]).cuda(), cache_params=cache,
+                    cache_position=torch.arange(L), attention_mask=torch.from_numpy(z["attention_mask"]).cuda())
+    assert relerr(out, torch.from_numpy(z["out"])) < 1e-4
+    assert relerr(cache.ssm, torch.from_numpy(z["ssm_state"])) < 1e-4
+    assert torch.equal(cache.conv.cpu(), torch.from_numpy(z["conv_state"]))

@@ -62,13 +62,31 @@ def test_tc_state_summary_matches_oracle(tv):
     assert relerr(fin, ref_fin) < TOL and relerr(logp, ref_lp) < 1e-4
 
 
-def test_tc_matches_simt_at_9b_dims_16k(tv):
-    """BASELINE.json configs[1]: Nanov2-9B layer, bf16, batch 1, seqlen 16K -- tensor-core path against the fp32
-    CUDA-core path on identical inputs (the CPU oracle covers shorter sequences above)."""
+def test_tc_matches_oracle_at_9b_dims_16k(tv):
+    """BASELINE.json configs[1]: Nanov2-9B layer, bf16, batch 1, seqlen 16K -- the tensor-core path against the CPU oracle
+    (the restatement of the reference's torch_forward, oracle/mamba2_ref.py) on identical inputs; ~3 s of CPU time."""
     b, L, H, G = 1, 16384, 128, 8
     x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(b, L, H, 80, G, 128, torch.bfloat16, seed=14)
     out, fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, dt_bias=dt_bias, dt_softplus=True,
                                             return_final_states=True)
-    ref, ref_fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, dt_bias=dt_bias, dt_softplus=True,
-                                                return_final_states=True, _force_simt=True)
+    assert tv.ssd_kernel_family(torch.bfloat16, 80, 128, 128) == "tcgen05"
+    ref, ref_fin = R.ssd_chunked_ref(*_cpu(x, dt, A, B, C), 128, D=D.cpu(), dt_bias=dt_bias.cpu(), dt_softplus=True)
     assert relerr(out, ref) < TOL and relerr(fin, ref_fin) < TOL
+    # the fp32 CUDA-core family on the same inputs (what fp32 callers and other shapes get) agrees as well
+    simt, simt_fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, D=D, dt_bias=dt_bias, dt_softplus=True,
+                                                  return_final_states=True, _force_simt=True)
+    assert relerr(simt, ref) < TOL and relerr(simt_fin, ref_fin) < TOL
+
+
+def test_reuse_dt_cumsum_refuses_a_workspace_filled_from_other_inputs(tv):
+    """`_reuse_dt_cumsum` skips the dt/cumsum pre-kernel and trusts the scratch of the previous call: the library tags
+    the scratch with the inputs it was computed from and must refuse a reuse that does not match."""
+    x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(1, 512, 8, 80, 2, 128, torch.bfloat16, seed=3)
+    kw = dict(D=D, dt_bias=dt_bias, dt_softplus=True, return_final_states=True)
+    out, fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, **kw)
+    out2, fin2 = tv.mamba_chunk_scan_combined(x, dt, A, B, C, 128, _reuse_dt_cumsum=True, **kw)     # same inputs: fine
+    assert torch.equal(out, out2) and torch.equal(fin, fin2)
+    with pytest.raises(ValueError, match="reuse_dt_cumsum"):                                         # another dt tensor
+        tv.mamba_chunk_scan_combined(x, dt.clone(), A, B, C, 128, _reuse_dt_cumsum=True, **kw)
+    with pytest.raises(ValueError, match="reuse_dt_cumsum"):                                         # other dims
+        tv.mamba_chunk_scan_combined(x[:, :256], dt[:, :256], A, B[:, :256], C[:, :256], 128, _reuse_dt_cumsum=True, **kw)

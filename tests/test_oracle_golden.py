@@ -146,3 +146,24 @@ def test_hybrid_stack_oracle_matches_reference_golden(path):
                                ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd,
                                group_map="torch_forward")
     assert relerr(out, d["last_hidden_state"]) < 2e-5
+
+
+def test_oracle_padding_mask_matches_reference_batch2(golden_dir):
+    """Batch 2, left-padded, attention_mask: the oracle applies apply_mask_to_padding_states where torch_forward does
+    (modeling_nano.py:676 and :707); golden vector from the reference's own forward (oracle/gen_golden.py::main_masked)."""
+    z = np.load(os.path.join(golden_dir, "masked_g1_batch2_leftpad37.npz"))
+    hidden, H, P, G, N, Q, L = [int(v) for v in z["dims"]]
+    sd = {k: torch.from_numpy(z[k]) for k in ("in_proj.weight", "conv1d.weight", "conv1d.bias", "dt_bias", "A_log", "D",
+                                               "norm.weight", "out_proj.weight")}
+    hs, mask = torch.from_numpy(z["hidden_states"]), torch.from_numpy(z["attention_mask"])
+    out, conv_state, ssm_state = R.mixer_forward_ref(sd, hs, num_heads=H, head_dim=P, n_groups=G, ssm_state_size=N,
+                                                     chunk_size=Q, group_map="torch_forward", attention_mask=mask)
+    ref = torch.from_numpy(z["out"])
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-5
+    ref_ssm = torch.from_numpy(z["ssm_state"])
+    assert float((ssm_state - ref_ssm).abs().max() / ref_ssm.abs().max()) < 2e-5
+    assert torch.equal(conv_state, torch.from_numpy(z["conv_state"]))
+    # without the second mask application the padded rows of sequence 0 leak silu(conv bias) into the state
+    out_nomask, _, _ = R.mixer_forward_ref(sd, hs * mask[:, :, None], num_heads=H, head_dim=P, n_groups=G,
+                                           ssm_state_size=N, chunk_size=Q, group_map="torch_forward")
+    assert float((out_nomask[0] - ref[0]).abs().max() / ref.abs().max()) > 1e-3

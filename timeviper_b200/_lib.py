@@ -74,7 +74,7 @@ class SsuParams(C.Structure):
 EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd",
            "tv_ssd_workspace_bytes", "tv_ssd_chunk_scan_fwd", "tv_ssd_kernel_family",
            "tv_ssd_fold_boundary_states", "tv_causal_conv1d_update", "tv_selective_state_update",
-           "tv_debug_set_trace", "tv_debug_set_ablate")
+           "tv_debug_set_trace", "tv_debug_set_ablate", "tv_debug_launch_count")
 
 _lib = None
 
@@ -112,6 +112,8 @@ def load():
     lib.tv_debug_set_trace.restype = None
     lib.tv_debug_set_ablate.argtypes = [C.c_int]
     lib.tv_debug_set_ablate.restype = None
+    lib.tv_debug_launch_count.argtypes = []
+    lib.tv_debug_launch_count.restype = C.c_ulonglong
     if lib.tv_abi_version() != TV_ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.tv_abi_version()} != {TV_ABI_VERSION} (rebuild the library)")
     _lib = lib

@@ -2,12 +2,17 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "ssd.h"
 
 namespace tv {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -70,3 +75,5 @@ extern "C" int tv_ssd_chunk_scan_fwd(const tv_ssd_params* p, void* workspace, si
 // Debug hook (not part of the reference-facing ABI): per-chunk clock64 stamps of CTA (0,0) of the fused SSD kernel.
 extern "C" void tv_debug_set_trace(void* device_buffer) { tv::set_trace_buffer(device_buffer); }
 extern "C" void tv_debug_set_ablate(int mask) { tv::set_ablate(mask); }
+// Number of kernels this library has enqueued so far in this process (all entry points, all streams).
+extern "C" unsigned long long tv_debug_launch_count(void) { return tv::launches_so_far(); }

@@ -10,6 +10,8 @@
 namespace tv {
 
 void set_error(const char* fmt, ...);
+// bookkeeping for tv_debug_launch_count(): every kernel this library enqueues is counted (bench.py reports it)
+void count_launches(int n);
 
 #define TV_CHECK_ARG(cond, ...)            \
   do {                                      \
@@ -26,6 +28,13 @@ void set_error(const char* fmt, ...);
       ::tv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
       return TV_ERR_CUDA;                                                                       \
     }                                                                                           \
+  } while (0)
+
+// after a kernel launch: count it (tv_debug_launch_count) and surface a launch error
+#define TV_LAUNCH_OK()            \
+  do {                            \
+    ::tv::count_launches(1);      \
+    TV_CUDA_OK(cudaGetLastError()); \
   } while (0)
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -157,7 +157,7 @@ static int launch_conv(const tv_conv1d_params& p, cudaStream_t s) {
                                      (const T*)p.initial_states, (T*)p.out, (T*)p.final_states, p.dim,
                                      p.seqlen, p.x_batch_stride, p.x_seq_stride, p.out_batch_stride,
                                      p.out_seq_stride);
-  TV_CUDA_OK(cudaGetLastError());
+  TV_LAUNCH_OK();
   return TV_OK;
 }
 

@@ -77,7 +77,7 @@ static int launch_conv_update(const tv_conv1d_update_params& p, cudaStream_t s) 
   auto k = p.silu ? conv1d_update_kernel<T, true> : conv1d_update_kernel<T, false>;
   k<<<grid, 256, 0, s>>>((const T*)p.x, (T*)p.conv_state, (const T*)p.weight, (const T*)p.bias, (T*)p.out, p.dim, p.width,
                          p.state_len, p.x_batch_stride, p.out_batch_stride, p.state_batch_stride, p.state_dim_stride);
-  TV_CUDA_OK(cudaGetLastError());
+  TV_LAUNCH_OK();
   return TV_OK;
 }
 
@@ -113,6 +113,6 @@ extern "C" int tv_selective_state_update(const tv_ssu_params* p, void* stream) {
     if (p->state_dtype == TV_F32) ssu_kernel<float, float><<<grid, 256, 0, s>>>(*p);
     else ssu_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(*p);
   }
-  TV_CUDA_OK(cudaGetLastError());
+  TV_LAUNCH_OK();
   return TV_OK;
 }

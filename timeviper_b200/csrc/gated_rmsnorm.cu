@@ -155,7 +155,7 @@ static int launch_norm(const tv_rmsnorm_params& p, cudaStream_t s) {
   else if (!hb) TV_NORM_LAUNCH(false, true, false);
   else TV_NORM_LAUNCH(false, true, true);
 #undef TV_NORM_LAUNCH
-  TV_CUDA_OK(cudaGetLastError());
+  TV_LAUNCH_OK();
   return TV_OK;
 }
 

@@ -403,7 +403,7 @@ int launch_dt_cumsum(const tv_ssd_params& p, float* dt_act, float* cs, cudaStrea
     ssd_dt_cumsum_kernel<float><<<grid, 128, Q * 33 * sizeof(float), s>>>(
         (const float*)p.dt, p.A, p.dt_bias, dt_act, cs, L, H, Q, nchunks, p.dt_batch_stride, p.dt_seq_stride,
         p.dt_head_stride, p.dt_softplus, p.dt_min, p.dt_max);
-  TV_CUDA_OK(cudaGetLastError());
+  TV_LAUNCH_OK();
   return TV_OK;
 }
 
@@ -432,14 +432,14 @@ static int run_simt(const tv_ssd_params& p, char* ws, cudaStream_t s) {
     k<<<grid, 256, smem, s>>>((const T*)p.x, (const T*)p.B, dt_act, cs, states, L, H, P, G, N, Q, nchunks,
                               p.x_batch_stride, p.x_seq_stride, p.x_head_stride, p.b_batch_stride,
                               p.b_seq_stride, p.b_group_stride);
-    TV_CUDA_OK(cudaGetLastError());
+    TV_LAUNCH_OK();
   }
   {
     const int PN = P * N;
     dim3 grid((unsigned)ceil_div(PN, 256), H, p.batch);
     ssd_state_passing_kernel<<<grid, 256, 0, s>>>(states, cs, p.initial_states, p.final_states, p.logdecay_sum,
                                                   H, PN, Q, nchunks, p.mode == TV_SSD_FULL ? 1 : 0);
-    TV_CUDA_OK(cudaGetLastError());
+    TV_LAUNCH_OK();
   }
   if (p.mode == TV_SSD_STATE_ONLY) return TV_OK;
   {
@@ -451,7 +451,7 @@ static int run_simt(const tv_ssd_params& p, char* ws, cudaStream_t s) {
     k<<<grid, 256, smem, s>>>((const T*)p.C, (const T*)p.B, CB, L, G, N, Q, nchunks, p.c_batch_stride,
                               p.c_seq_stride, p.c_group_stride, p.b_batch_stride, p.b_seq_stride,
                               p.b_group_stride);
-    TV_CUDA_OK(cudaGetLastError());
+    TV_LAUNCH_OK();
   }
   {
     const size_t smem =
@@ -467,7 +467,7 @@ static int run_simt(const tv_ssd_params& p, char* ws, cudaStream_t s) {
                               (T*)p.out, L, H, P, G, N, Q, nchunks, p.x_batch_stride, p.x_seq_stride,
                               p.x_head_stride, p.c_batch_stride, p.c_seq_stride, p.c_group_stride,
                               p.z_batch_stride, p.z_seq_stride, p.z_head_stride, p.d_has_hdim);
-    TV_CUDA_OK(cudaGetLastError());
+    TV_LAUNCH_OK();
   }
   return TV_OK;
 }
@@ -520,6 +520,6 @@ extern "C" int tv_ssd_fold_boundary_states(const float* states, const float* log
   dim3 grid((unsigned)ceil_div(PN / 4, 256), (unsigned)BH);
   fold_boundary_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(states, logdecay, initial, out, rank, srs, lrs,
                                                               (int)(PN / 4));
-  TV_CUDA_OK(cudaGetLastError());
+  TV_LAUNCH_OK();
   return TV_OK;
 }

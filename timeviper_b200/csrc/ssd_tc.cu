@@ -27,6 +27,9 @@
 #include "ssd.h"
 #include "tmap.h"
 
+#include <mutex>
+#include <unordered_map>
+
 namespace tv {
 using namespace sm100;
 
@@ -815,6 +818,23 @@ static int g_ablate = 0;
 void set_ablate(int m) { g_ablate = m; }
 static void* g_trace_ptr = nullptr;   // debug: device buffer of nchunks*16 int64 (tv_debug_set_trace)
 void set_trace_buffer(void* p) { g_trace_ptr = p; }
+// what the dt / cumsum arrays in a workspace were computed from (see reuse_dt_cumsum below)
+struct DtTag {
+  const void *dt, *A, *bias;
+  int batch, seqlen, nheads;
+  int64_t sb, ss, sh;
+  int softplus;
+  float lo, hi;
+  bool operator==(const DtTag& o) const {
+    // A and dt_bias are often fp32 temporaries of bf16 parameters (a new address per call): compared by presence only
+    return dt == o.dt && (A == nullptr) == (o.A == nullptr) && (bias == nullptr) == (o.bias == nullptr) &&
+           batch == o.batch && seqlen == o.seqlen && nheads == o.nheads && sb == o.sb && ss == o.ss && sh == o.sh &&
+           softplus == o.softplus && lo == o.lo && hi == o.hi;
+  }
+};
+static std::mutex g_dt_tags_mu;
+static std::unordered_map<const void*, DtTag> g_dt_tags;
+
 bool tc_supported(const tv_ssd_params& p) {
   if (p.dtype != TV_BF16 || p.headdim != tc::P || p.dstate != tc::N || p.chunk_size != tc::Q) return false;
   if (p.nheads % p.ngroups != 0) return false;
@@ -841,6 +861,25 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
   const size_t per = (((size_t)p.batch * nchunks * p.nheads * Q * sizeof(float)) + 255) & ~(size_t)255;
   float* dt_act = (float*)workspace;
   float* cs = (float*)((char*)workspace + per);
+  // `reuse_dt_cumsum` trusts that `workspace` still holds dt / cumsum of a previous call: remember which inputs the
+  // arrays in a given workspace were computed from and refuse a reuse that does not match (another dt tensor, other dims
+  // or strides, another limit, or a workspace this library has never filled).  Contents changed in place behind the same
+  // pointer, or other A / dt_bias values, cannot be seen from here.
+  {
+    const DtTag tag{p.dt, p.A, p.dt_bias, p.batch, p.seqlen, p.nheads, p.dt_batch_stride, p.dt_seq_stride,
+                    p.dt_head_stride, p.dt_softplus, p.dt_min, p.dt_max};
+    std::lock_guard<std::mutex> lock(g_dt_tags_mu);
+    if (!p.reuse_dt_cumsum) {
+      g_dt_tags[workspace] = tag;
+    } else {
+      auto it = g_dt_tags.find(workspace);
+      if (it == g_dt_tags.end() || !(it->second == tag)) {
+        set_error("ssd: reuse_dt_cumsum, but this workspace does not hold the dt/cumsum arrays of these inputs "
+                  "(another dt tensor, other dims / strides / dt limits, or a reallocated workspace)");
+        return TV_ERR_INVALID;
+      }
+    }
+  }
   if (!p.reuse_dt_cumsum) {
     int rc = launch_dt_cumsum(p, dt_act, cs, s);
     if (rc != TV_OK) return rc;
@@ -907,7 +946,7 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
     int* first_chunk = (int*)((char*)workspace + 2 * per);
     const int BH = p.batch * p.nheads;
     ssd_suffix_scan_kernel<<<(BH + 3) / 4, 128, 0, s>>>(cs, p.logdecay_sum, first_chunk, BH, p.nheads, nchunks, Q);
-    TV_CUDA_OK(cudaGetLastError());
+    TV_LAUNCH_OK();
     TV_CUDA_OK(cudaFuncSetAttribute(ssd_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st::SMEM_BYTES));
     // two CTAs per head (each half of the chunk walk) once the walk is long enough to pay for zeroing the output
     const int split = nchunks >= 16 ? 2 : 1;
@@ -919,7 +958,7 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
   else if (p.z != nullptr) lrc = dfold ? launch(ssd_fused_kernel<true, true, true>) : launch(ssd_fused_kernel<true, true, false>);
   else lrc = dfold ? launch(ssd_fused_kernel<true, false, true>) : launch(ssd_fused_kernel<true, false, false>);
   if (lrc != TV_OK) return lrc;
-  TV_CUDA_OK(cudaGetLastError());
+  TV_LAUNCH_OK();
   return TV_OK;
 }
 

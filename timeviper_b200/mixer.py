@@ -74,6 +74,20 @@ class Mamba2MixerPrefill(nn.Module):
         nn.init.kaiming_uniform_(self.out_proj.weight, a=math.sqrt(5))
         self.out_proj.weight /= math.sqrt(c.num_hidden_layers)
 
+    def invalidate_param_caches(self):
+        """Drop the cached fp32 images of A_log / D / dt_bias.  Called on load_state_dict and on .to()/.cuda(); call it
+        by hand after writing through ``param.data`` (such writes do not bump the version counter the caches key on)."""
+        self.__dict__.pop("_A_key", None)
+        self.__dict__.pop("_f32_cache", None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_param_caches()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_param_caches()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def decay_rates(self):
         """A = -exp(A_log) in fp32 (modeling_nano.py:550-552), recomputed only when A_log changes."""
         key = (self.A_log._version, self.A_log.data_ptr())
@@ -96,7 +110,7 @@ class Mamba2MixerPrefill(nn.Module):
 
     # -- the three-kernel core, on an already projected input (what bench.py's `value` times) ------------
     def scan_core(self, projected_states, cache_params=None, conv_initial_states=None, ssm_initial_states=None,
-                  return_states=False, return_conv_state=False):
+                  return_states=False, return_conv_state=False, attention_mask=None):
         """projected_states (b, L, d_inner + conv_dim + H) -> normed scan output (b, L, d_inner).
         With return_states: (y, ssm_state[, conv_final_states (b, conv_dim, K-1)])."""
         batch_size, seq_len, _ = projected_states.shape
@@ -114,6 +128,9 @@ class Mamba2MixerPrefill(nn.Module):
         if return_conv_state:
             conv_out, conv_final = conv_out
         hidden_states_B_C = conv_out.transpose(1, 2)
+        if attention_mask is not None and batch_size > 1 and seq_len > 1:       # :625-627 (apply_mask_to_padding_states)
+            # padded positions leave the conv as silu(bias) != 0: zero them again before they reach x, B and C
+            hidden_states_B_C.mul_(attention_mask[:, :, None].to(hidden_states_B_C.dtype))
         hidden_states, B, C = torch.split(hidden_states_B_C, [self.intermediate_size, gts, gts], dim=-1)
         A = self.decay_rates()                                                  # :550-552
         scan_output, ssm_state = ops.mamba_chunk_scan_combined(                 # :639-653
@@ -129,6 +146,28 @@ class Mamba2MixerPrefill(nn.Module):
         if return_states:
             return (scan_output, ssm_state, conv_final) if return_conv_state else (scan_output, ssm_state)
         return scan_output
+
+    @torch.no_grad()
+    def scan_core_graph(self, projected_states):
+        """``scan_core`` replayed as ONE CUDA graph launch (conv, dt/cumsum, fused scan, norm): removes the launch gaps and
+        the Python/ctypes time between the four kernels (~0.15 ms per step at 128K tokens).  The graph is captured on first
+        use for this input tensor (address, shape, dtype) and re-captured if any of them changes; the returned tensor is
+        the graph's static output and is overwritten by the next replay."""
+        key = (projected_states.data_ptr(), tuple(projected_states.shape), projected_states.dtype,
+               tuple(projected_states.stride()))
+        held = self.__dict__.get("_scan_graph")
+        if held is None or held[0] != key:
+            side = torch.cuda.Stream(projected_states.device)
+            side.wait_stream(torch.cuda.current_stream(projected_states.device))
+            with torch.cuda.stream(side):                 # warm-up off the capture: parameter caches, lazy CUDA state
+                self.scan_core(projected_states)
+            torch.cuda.current_stream(projected_states.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.scan_core(projected_states)
+            held = self.__dict__["_scan_graph"] = (key, graph, out)
+        held[1].replay()
+        return held[2]
 
     @staticmethod
     def _segment_bounds(L, seg, chunk):
@@ -150,7 +189,7 @@ class Mamba2MixerPrefill(nn.Module):
         return bounds
 
     @torch.no_grad()
-    def prefill_from_host(self, hidden_host, out_host=None, segment_tokens=16384, cache_params=None):
+    def prefill_from_host(self, hidden_host, out_host=None, segment_tokens=16384, cache_params=None, attention_mask=None):
         """Prefill a (b, L, hidden) sequence that lives in (pinned) HOST memory and return the mixer output in
         pinned host memory.  The sequence is streamed through the GPU in segments: the H2D copy of segment i+1, the
         mixer on segment i (in_proj -> conv -> SSD -> norm -> out_proj, continued from the carried conv/SSM
@@ -160,6 +199,8 @@ class Mamba2MixerPrefill(nn.Module):
         ``initial_states`` of mamba_chunk_scan_combined); same cache side effects."""
         dev = self.in_proj.weight.device
         b, L, hidden = hidden_host.shape
+        if attention_mask is not None and b > 1 and L > 1:
+            raise NotImplementedError("prefill_from_host streams unpadded sequences; use forward() for a padded batch")
         seg = max(self.chunk_size, (int(segment_tokens) // self.chunk_size) * self.chunk_size)
         if out_host is None:
             out_host = torch.empty((b, L, self.hidden_size), dtype=hidden_host.dtype).pin_memory()
@@ -250,7 +291,7 @@ class Mamba2MixerPrefill(nn.Module):
             # apply_mask_to_padding_states, modeling_nano.py:189-201 (a no-op at batch 1)
             hidden_states = (hidden_states * attention_mask[:, :, None]).to(hidden_states.dtype)
         projected_states = self.in_proj(hidden_states)                          # :472
-        scan_output = self.scan_core(projected_states, cache_params)
+        scan_output = self.scan_core(projected_states, cache_params, attention_mask=attention_mask)
         return self.out_proj(scan_output)                                       # :667
 
 

@@ -154,6 +154,29 @@ def _workspace(nbytes, device, owner_stream=None):
     return ws
 
 
+simt_fallbacks = 0          # bf16 SSD calls served by the fp32 CUDA-core family (see _warn_simt_fallback)
+_simt_warned = set()
+
+
+def _warn_simt_fallback(headdim, dstate, chunk_size):
+    """The tcgen05 kernel is specialised for (bf16, headdim 80, dstate 128, chunk 128) with 16-byte aligned rows; every other
+    bf16 call runs on the CUDA-core family, which is 50-60x slower at the 9B geometry.  Say so once per shape and count."""
+    global simt_fallbacks
+    simt_fallbacks += 1
+    key = (headdim, dstate, chunk_size)
+    if key not in _simt_warned:
+        _simt_warned.add(key)
+        import warnings
+        warnings.warn(f"timeviper_b200: bf16 SSD scan with headdim={headdim}, dstate={dstate}, chunk_size={chunk_size} "
+                      "(or unaligned views) is not served by the tcgen05 kernel (80/128/128); using the fp32 CUDA-core "
+                      "kernels, which are far slower at large sizes", RuntimeWarning, stacklevel=4)
+
+
+def launch_count():
+    """Kernels libtimeviper_b200.so has enqueued so far in this process (all ops, all streams)."""
+    return int(L.load().tv_debug_launch_count())
+
+
 def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_softplus, dt_limit, mode,
               force_simt=False, want_final=True, want_logdecay=False, reuse_dt_cumsum=False, final_out=None,
               logdecay_out=None, workspace_stream=None):
@@ -222,6 +245,8 @@ def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_sof
         dt_min=lo, dt_max=hi if math.isfinite(hi) else float("inf"), dtype=code, mode=mode,
         force_simt=int(bool(force_simt)), reuse_dt_cumsum=int(bool(reuse_dt_cumsum)))
     lib = L.load()
+    if code == L.TV_BF16 and not force_simt and lib.tv_ssd_kernel_family(C.byref(p)) == 0:
+        _warn_simt_fallback(headdim, dstate, int(chunk_size))
     need = lib.tv_ssd_workspace_bytes(C.byref(p))
     ws = _workspace(need, dev, workspace_stream)
     L.check(lib.tv_ssd_chunk_scan_fwd(C.byref(p), _ptr(ws), ws.numel(), _stream(x)), "mamba_chunk_scan_combined")

@@ -48,10 +48,12 @@ def _all_gather_rows(send, group):
     return out
 
 
-def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, ops=_cuda_ops):
+def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, ops=_cuda_ops, attention_mask=None):
     """The three-kernel core of ``Mamba2MixerPrefill.scan_core`` on this rank's shard of the sequence."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     b, L, _ = projected_states.shape
+    if attention_mask is not None and b > 1 and L > 1:
+        raise NotImplementedError("the sequence-sharded path takes unpadded sequences (the reference is batch-1 here)")
     K = mixer.conv_kernel_size
     H, P, G, N = mixer.num_heads, mixer.head_dim, mixer.n_groups, mixer.ssm_state_size
     gate, xBC, dt = projected_states.split([mixer.intermediate_size, mixer.conv_dim, H], dim=-1)
