@@ -45,8 +45,19 @@ def load():
     for pth in (os.path.join(HERE, "_shim"), os.path.abspath(DST_ROOT)):
         if pth not in sys.path:
             sys.path.insert(0, pth)
-    import nano.modeling_nano as mn
-    from nano.configuration_nano import NemotronHConfig
+    # On a GPU box transformers' is_mamba_2_ssm_available() finds the shim package and then fails to parse its version
+    # ('N/A': the shim has no distribution metadata).  The wheels are absent either way, so the harness answers "not
+    # available" for the duration of the import -- the reference module then binds None to the operator names
+    # (modeling_nano.py:66-71, :82), exactly what it does in the CPU container; patch_reference rebinds them afterwards.
+    import transformers.utils.import_utils as iu
+    saved = (iu.is_mamba_2_ssm_available, iu.is_causal_conv1d_available)
+    iu.is_mamba_2_ssm_available = lambda: False
+    iu.is_causal_conv1d_available = lambda: False
+    try:
+        import nano.modeling_nano as mn
+        from nano.configuration_nano import NemotronHConfig
+    finally:
+        iu.is_mamba_2_ssm_available, iu.is_causal_conv1d_available = saved
     return mn, NemotronHConfig
 
 
