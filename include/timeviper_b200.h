@@ -144,6 +144,14 @@ int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, cons
                                 int32_t headdim, int32_t dstate, int64_t states_rank_stride,
                                 int64_t logdecay_rank_stride, void* stream);
 
+/* The same fold with every rank's summary read through ITS OWN pointer: state_ptrs[r] / logdecay_ptrs[r] (HOST arrays of
+ * `rank` device pointers, r < rank) may be peer memory of other GPUs of the node (CUDA IPC / symmetric memory mapped
+ * into this process), so the boundary-state exchange and the fold are one kernel over NVLink.  Summaries whose weight
+ * has underflowed fp32 are not fetched.  New work; at most 16 ranks. */
+int tv_ssd_fold_boundary_states_p2p(const void* const* state_ptrs, const void* const* logdecay_ptrs, const float* initial,
+                                    float* out, int32_t rank, int32_t batch, int32_t nheads, int32_t headdim,
+                                    int32_t dstate, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Single-token decode step: the two operators the reference's cached branch calls,
  * modeling_nano.py:495-501 and :528-539, consuming the states the prefill path leaves in the cache.

@@ -73,7 +73,7 @@ class SsuParams(C.Structure):
 
 EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd",
            "tv_ssd_workspace_bytes", "tv_ssd_chunk_scan_fwd", "tv_ssd_kernel_family",
-           "tv_ssd_fold_boundary_states", "tv_causal_conv1d_update", "tv_selective_state_update",
+           "tv_ssd_fold_boundary_states", "tv_ssd_fold_boundary_states_p2p", "tv_causal_conv1d_update", "tv_selective_state_update",
            "tv_debug_set_trace", "tv_debug_set_ablate", "tv_debug_launch_count")
 
 _lib = None
@@ -104,6 +104,9 @@ def load():
                                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                                 C.c_void_p]
     lib.tv_ssd_fold_boundary_states.restype = C.c_int
+    lib.tv_ssd_fold_boundary_states_p2p.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.tv_ssd_fold_boundary_states_p2p.restype = C.c_int
     lib.tv_causal_conv1d_update.argtypes = [C.POINTER(ConvUpdateParams), C.c_void_p]
     lib.tv_causal_conv1d_update.restype = C.c_int
     lib.tv_selective_state_update.argtypes = [C.POINTER(SsuParams), C.c_void_p]

@@ -501,7 +501,89 @@ fold_boundary_kernel(const float* __restrict__ states, const float* __restrict__
   reinterpret_cast<float4*>(out)[off] = s;
 }
 
+// The same fold reading each rank's summary THROUGH ITS OWN POINTER -- peer memory of the other GPUs (NVLink / NVSwitch
+// loads), no gathered copy: the boundary-state exchange and the fold are one kernel.  The decay chain is walked from
+// rank-1 downwards first: once the accumulated log-decay is below the fp32 underflow point the earlier summaries would be
+// multiplied by exactly 0, so they are never fetched -- with realistic decay rates a rank reads little more than its
+// left neighbour's 5 MB instead of all rank*5 MB.
+struct FoldPeers {
+  const float* s[16];
+  const float* lp[16];
+};
+
+// one block per (b, h); FOLD_E float4 per thread are in flight at a time (peer loads have ~2 us of latency: the kernel is
+// a copy with as many independent loads outstanding as the registers allow, not a chain of dependent round trips)
+constexpr int FOLD_E = 10;
+__global__ void __launch_bounds__(256)
+fold_boundary_p2p_kernel(const FoldPeers peers, const float* __restrict__ init, float* __restrict__ out, int rank, int PN4) {
+  const int64_t bh = blockIdx.x;
+  // all log-decays of the earlier ranks at once (independent loads, one round trip)
+  float lp[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) lp[r] = r < rank ? __ldg(peers.lp[r] + bh) : 0.f;
+  // first summary whose weight exp(sum of logdecay of the ranks after it) is still representable
+  int j0 = rank;                       // rank: "start from init"
+  float acc_log = 0.f;
+#pragma unroll
+  for (int r = 15; r >= 0; --r)
+    if (r < rank && acc_log >= -104.f) { j0 = r; acc_log += lp[r]; }
+  const bool init_live = acc_log >= -104.f && init != nullptr;
+  const float4* ini = reinterpret_cast<const float4*>(init) + bh * PN4;
+  float4* dst = reinterpret_cast<float4*>(out) + bh * PN4;
+  for (int e0 = threadIdx.x; e0 < PN4; e0 += 256 * FOLD_E) {
+    float4 s[FOLD_E];
+#pragma unroll
+    for (int i = 0; i < FOLD_E; ++i) {
+      const int e = e0 + i * 256;
+      s[i] = (init_live && e < PN4) ? ini[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int r = j0; r < rank; ++r) {
+      const float d = expf(lp[r]);
+      const float4* src = reinterpret_cast<const float4*>(peers.s[r]) + bh * PN4;
+      float4 v[FOLD_E];
+#pragma unroll
+      for (int i = 0; i < FOLD_E; ++i) {
+        const int e = e0 + i * 256;
+        v[i] = e < PN4 ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < FOLD_E; ++i) {
+        s[i].x = fmaf(d, s[i].x, v[i].x); s[i].y = fmaf(d, s[i].y, v[i].y);
+        s[i].z = fmaf(d, s[i].z, v[i].z); s[i].w = fmaf(d, s[i].w, v[i].w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < FOLD_E; ++i) {
+      const int e = e0 + i * 256;
+      if (e < PN4) dst[e] = s[i];
+    }
+  }
+}
+
 }  // namespace tv
+
+extern "C" int tv_ssd_fold_boundary_states_p2p(const void* const* state_ptrs, const void* const* logdecay_ptrs,
+                                               const float* initial, float* out, int32_t rank, int32_t batch,
+                                               int32_t nheads, int32_t headdim, int32_t dstate, void* stream) {
+  using namespace tv;
+  TV_CHECK_ARG(out != nullptr && rank >= 0 && rank <= 16 && batch > 0 && nheads > 0 && headdim > 0 && dstate > 0,
+               "fold_boundary_states_p2p: bad arguments (at most 16 ranks)");
+  TV_CHECK_ARG(rank == 0 || (state_ptrs != nullptr && logdecay_ptrs != nullptr), "fold_boundary_states_p2p: null pointer tables");
+  const int64_t PN = (int64_t)headdim * dstate, BH = (int64_t)batch * nheads;
+  FoldPeers peers;
+  for (int r = 0; r < 16; ++r) {
+    peers.s[r] = r < rank ? (const float*)state_ptrs[r] : nullptr;
+    peers.lp[r] = r < rank ? (const float*)logdecay_ptrs[r] : nullptr;
+    if (r < rank)
+      TV_CHECK_ARG(peers.s[r] != nullptr && peers.lp[r] != nullptr && (uintptr_t)peers.s[r] % 16 == 0,
+                   "fold_boundary_states_p2p: summary pointer of rank %d is null or not 16-byte aligned", r);
+  }
+  TV_CHECK_ARG(PN % 4 == 0 && (uintptr_t)out % 16 == 0 && (initial == nullptr || (uintptr_t)initial % 16 == 0),
+               "fold_boundary_states_p2p: headdim*dstate must be a multiple of 4, out/initial 16-byte aligned");
+  fold_boundary_p2p_kernel<<<(unsigned)BH, 256, 0, (cudaStream_t)stream>>>(peers, initial, out, rank, (int)(PN / 4));
+  TV_LAUNCH_OK();
+  return TV_OK;
+}
 
 extern "C" int tv_ssd_fold_boundary_states(const float* states, const float* logdecay, const float* initial,
                                            float* out, int32_t rank, int32_t batch, int32_t nheads,

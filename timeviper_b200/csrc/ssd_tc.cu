@@ -27,6 +27,7 @@
 #include "ssd.h"
 #include "tmap.h"
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -686,12 +687,15 @@ enum Bar { FULL0 = 0, EMPTY0 = FULL0 + NST, SCALED0 = EMPTY0 + NST, DONE = SCALE
 static_assert(OFF_X % 1024 == 0 && 2 * SMEM_BYTES <= 226 * 1024, "state kernel smem: two CTAs per SM");
 }  // namespace st
 
-// grid (H, batch, split).  Part z of `split` handles the visited-chunk indices [count*z/split, count*(z+1)/split) of the
+constexpr int kMaxStateSplit = 8;
+// grid (H, batch, split).  Part z of `split` handles the visited-chunk indices [total*z/split, total*(z+1)/split) of the
 // backwards walk n-1, n-2, ..., c_first; because the decay is taken relative to the END of the shard the partial states
-// simply add up: with split == 2 both parts red.add onto a zeroed output (two addends: order-independent, bit-stable).
+// simply add up.  With split > 1 every part with work writes its partial state to `partial` [(b,h)][part][P][N] and
+// ssd_state_reduce_kernel adds the parts in a fixed order (no atomics: the summary is bit-reproducible); a long walk
+// (a slowly decaying head) is then `split` short chains on different SMs instead of one chain of nchunks steps.
 __global__ void __launch_bounds__(st::THREADS, 2)
 ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const int* __restrict__ first_chunk,
-                 const int split) {
+                 const int split, float* __restrict__ partial) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -705,7 +709,7 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
   const int total = n - c_first;                       // chunks n-1, n-2, ..., c_first
   const int i_begin = (int)((int64_t)total * part / split), i_end = (int)((int64_t)total * (part + 1) / split);
   const int count = i_end - i_begin;
-  if (count == 0 && split > 1) return;                 // nothing to add (the output was zeroed by the host)
+  if (count == 0 && split > 1) return;                 // no partial state: the reduction skips this part
   if (threadIdx.x == 0) {
     for (int i = 0; i < st::NST; ++i) {
       mbar_init(&bars[st::FULL0 + i], 1); mbar_init(&bars[st::EMPTY0 + i], 1); mbar_init(&bars[st::SCALED0 + i], 4);
@@ -801,16 +805,34 @@ ssd_state_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a, const 
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = 0u;       // split == 1 and no live chunk: the summary is exactly zero
       }
+      float* dst = split > 1 ? partial + ((((int64_t)b * a.H + h) * split + part) * P + pc * 16) * N + r
+                             : a.fin + (((int64_t)b * a.H + h) * P + pc * 16) * N + r;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        float* dst = &a.fin[(((int64_t)b * a.H + h) * P + pc * 16 + k) * N + r];
-        if (split > 1) atomicAdd(dst, __uint_as_float(v[k])); else *dst = __uint_as_float(v[k]);
-      }
+      for (int k = 0; k < 16; ++k) dst[(int64_t)k * N] = __uint_as_float(v[k]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<128>(tmem);
+}
+
+// out[b,h] = sum over the parts that had work, in part order (the same partition arithmetic as ssd_state_kernel)
+__global__ void __launch_bounds__(256)
+ssd_state_reduce_kernel(const float* __restrict__ partial, const int* __restrict__ first_chunk, float* __restrict__ out,
+                        int nchunks, int split, int PN4) {
+  const int64_t bh = blockIdx.y;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= PN4) return;
+  const int total = nchunks - first_chunk[bh];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int part = 0; part < split; ++part) {
+    const int i_begin = (int)((int64_t)total * part / split), i_end = (int)((int64_t)total * (part + 1) / split);
+    if (i_end > i_begin) {
+      const float4 v = reinterpret_cast<const float4*>(partial)[(bh * split + part) * PN4 + e];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  reinterpret_cast<float4*>(out)[bh * PN4 + e] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -852,7 +874,10 @@ bool tc_supported(const tv_ssd_params& p) {
 size_t tc_workspace_bytes(const tv_ssd_params& p) {
   const int64_t nchunks = ceil_div(p.seqlen, p.chunk_size);
   const size_t per = (size_t)p.batch * nchunks * p.nheads * p.chunk_size * sizeof(float);
-  return 2 * ((per + 255) & ~(size_t)255) + (((size_t)p.batch * p.nheads * sizeof(int)) + 255 & ~(size_t)255);
+  // dt | cumsum | first_chunk | partial shard summaries.  The size does not depend on `mode`: the sharded path calls
+  // DT_ONLY, STATE_ONLY and FULL on ONE workspace (reuse_dt_cumsum), which must not be re-allocated in between.
+  return 2 * ((per + 255) & ~(size_t)255) + ((((size_t)p.batch * p.nheads * sizeof(int)) + 255) & ~(size_t)255) +
+         (size_t)p.batch * p.nheads * kMaxStateSplit * tc::P * tc::N * sizeof(float);
 }
 
 int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
@@ -948,11 +973,16 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
     ssd_suffix_scan_kernel<<<(BH + 3) / 4, 128, 0, s>>>(cs, p.logdecay_sum, first_chunk, BH, p.nheads, nchunks, Q);
     TV_LAUNCH_OK();
     TV_CUDA_OK(cudaFuncSetAttribute(ssd_state_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st::SMEM_BYTES));
-    // two CTAs per head (each half of the chunk walk) once the walk is long enough to pay for zeroing the output
-    const int split = nchunks >= 16 ? 2 : 1;
-    if (split > 1)
-      TV_CUDA_OK(cudaMemsetAsync(p.final_states, 0, (size_t)p.batch * p.nheads * P * N * sizeof(float), s));
-    ssd_state_kernel<<<dim3(p.nheads, p.batch, split), st::THREADS, st::SMEM_BYTES, s>>>(maps, a, first_chunk, split);
+    // up to 8 CTAs per head, >= 8 chunks of the walk each
+    const int split = std::max(1, std::min(kMaxStateSplit, nchunks / 8));
+    float* partial = (float*)((char*)workspace + 2 * per + ((((size_t)BH * sizeof(int)) + 255) & ~(size_t)255));
+    ssd_state_kernel<<<dim3(p.nheads, p.batch, split), st::THREADS, st::SMEM_BYTES, s>>>(maps, a, first_chunk, split, partial);
+    if (split > 1) {
+      TV_LAUNCH_OK();
+      const int PN4 = P * N / 4;
+      ssd_state_reduce_kernel<<<dim3((unsigned)ceil_div(PN4, 256), (unsigned)BH), 256, 0, s>>>(partial, first_chunk,
+                                                                                            p.final_states, nchunks, split, PN4);
+    }
     lrc = TV_OK;
   }
   else if (p.z != nullptr) lrc = dfold ? launch(ssd_fused_kernel<true, true, true>) : launch(ssd_fused_kernel<true, true, false>);

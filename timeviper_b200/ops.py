@@ -321,6 +321,22 @@ def fold_boundary_states(states, logdecay, rank, initial_states=None):
     return out
 
 
+def fold_boundary_states_p2p(state_ptrs, logdecay_ptrs, rank, shape, device, initial_states=None):
+    """The fold of ``fold_boundary_states`` with the summary of rank r read through its own device pointer
+    ``state_ptrs[r]`` / ``logdecay_ptrs[r]`` (ints; peer memory mapped into this process, r < rank): exchange and fold in
+    one kernel over NVLink.  shape = (b, H, P, N).  Returns the state entering shard `rank`."""
+    b, H, P, N = shape
+    rank = int(rank)
+    sp = (C.c_void_p * max(rank, 1))(*[C.c_void_p(int(v)) for v in state_ptrs[:rank]])
+    lp = (C.c_void_p * max(rank, 1))(*[C.c_void_p(int(v)) for v in logdecay_ptrs[:rank]])
+    init = None if initial_states is None else initial_states.to(torch.float32).contiguous()
+    out = torch.empty((b, H, P, N), dtype=torch.float32, device=device)
+    L.check(L.load().tv_ssd_fold_boundary_states_p2p(sp, lp, _ptr(init), _ptr(out), rank, b, H, P, N,
+                                                     C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+            "fold_boundary_states_p2p")
+    return out
+
+
 def ssd_kernel_family(dtype, headdim, dstate, chunk_size, nheads=128, ngroups=8):
     """'tcgen05' or 'simt': which kernel family serves this shape (introspection for tests/bench)."""
     p = L.SsdParams(batch=1, seqlen=chunk_size, nheads=nheads, headdim=headdim, ngroups=ngroups, dstate=dstate,

@@ -48,6 +48,105 @@ def _all_gather_rows(send, group):
     return out
 
 
+class PeerExchange:
+    """Symmetric-memory buffers of the two exchanges of a sharded layer (one object per (group, device, shapes)):
+
+      * `flat`  [2][S_r | log P_r] fp32: the shard summary is written by the state kernel straight into this rank's
+        buffer; after one device-side barrier every rank folds the summaries it needs by reading its peers' buffers
+        over NVLink inside the fold kernel (ops.fold_boundary_states_p2p) -- no all-gather, no gathered copy;
+      * `halo`  [2][b, K-1, conv_dim]: rank r stores the last K-1 pre-conv rows of its shard into rank r+1's buffer
+        (one small peer copy) and signals it.
+
+    Both are double-buffered by step parity: a rank that is a step ahead writes the other half, and it cannot be two
+    steps ahead because every step ends with the barrier."""
+
+    def __init__(self, group, device, b, H, P, N, halo_shape, halo_dtype):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n = b * H * P * N
+        self.per = self.n + b * H
+        self.per_al = (self.per + 63) // 64 * 64                       # keep the second half 256-byte aligned
+        self.flat = symm.empty(2 * self.per_al, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.flat, self.group)
+        self.halo_elems = 1
+        for v in halo_shape:
+            self.halo_elems *= v
+        self.halo_al = (self.halo_elems + 127) // 128 * 128
+        self.halo = symm.empty(2 * self.halo_al, dtype=halo_dtype, device=device)
+        self.halo_hdl = symm.rendezvous(self.halo, self.group)
+        self.halo_shape, self.shape = tuple(halo_shape), (b, H, P, N)
+        self.step = 0
+        self.itemsize = self.halo.element_size()
+
+    def summary_views(self, parity):
+        base = self.flat[parity * self.per_al: parity * self.per_al + self.per]
+        b, H, P, N = self.shape
+        return base[:self.n].view(b, H, P, N), base[self.n:].view(b, H)
+
+    def peer_ptrs(self, parity):
+        off = parity * self.per_al * 4
+        sp = [int(p) + off for p in self.hdl.buffer_ptrs]
+        return sp, [p + self.n * 4 for p in sp]
+
+    def send_halo(self, rows, parity):
+        """rows (b, K-1, conv_dim) -> the halo buffer of rank+1, then signal it (stream-ordered)."""
+        if self.rank + 1 < self.world:
+            dst = self.halo_hdl.get_buffer(self.rank + 1, self.halo_shape, self.halo.dtype, parity * self.halo_al)
+            dst.copy_(rows)
+            self.halo_hdl.put_signal(self.rank + 1, channel=parity)
+
+    def recv_halo(self, parity):
+        """Wait for rank-1's rows; returns the local (b, K-1, conv_dim) buffer (None on rank 0)."""
+        if self.rank == 0:
+            return None
+        self.halo_hdl.wait_signal(self.rank - 1, channel=parity)
+        return self.halo[parity * self.halo_al: parity * self.halo_al + self.halo_elems].view(self.halo_shape)
+
+
+_exchanges = {}
+_p2p_disabled = [False]
+
+
+def _peer_exchange(group, dev, b, H, P, N, halo_shape, halo_dtype):
+    """The PeerExchange for these shapes, or None where symmetric memory is not usable (then NCCL all-gathers are used)."""
+    import os
+    if _p2p_disabled[0] or os.environ.get("TV_SHARDED_EXCHANGE", "p2p").lower() == "nccl":
+        return None
+    key = (id(group), dev.index, b, H, P, N, tuple(halo_shape), halo_dtype)
+    ex = _exchanges.get(key)
+    if ex is None:
+        try:
+            ex = PeerExchange(group, dev, b, H, P, N, halo_shape, halo_dtype)
+        except Exception as e:             # no P2P / fabric support on this box: keep the collective transport
+            import warnings
+            warnings.warn(f"timeviper_b200: symmetric-memory exchange unavailable ({type(e).__name__}: {e}); "
+                          "falling back to NCCL all-gathers for the boundary exchange")
+            _p2p_disabled[0] = True
+            return None
+        _exchanges[key] = ex
+    return ex
+
+
+def _gathered_fold(ops, native, mixer, x, dt, A, B, scan_kw, b, H, P, N, n, xBC_c, dev, group, rank, world):
+    """Collective transport of the boundary exchange (NCCL / gloo): summary into one flat buffer, ONE all-gather, fold."""
+    flat = torch.empty(n + b * H, dtype=torch.float32 if native else xBC_c.dtype, device=dev)
+    S_r, logP_r = flat[:n].view(b, H, P, N), flat[n:].view(b, H)
+    if native:
+
+        ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, _reuse_dt_cumsum=True, out=(S_r, logP_r),
+                                      **scan_kw)
+    else:
+        s, lp = ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, **scan_kw)
+        S_r.copy_(s)
+        logP_r.copy_(lp)
+    gathered = _all_gather_rows(flat, group)                          # (world, n + b*H)
+    S_all = gathered[:, :n].view(world, b, H, P, N)
+    logP_all = gathered[:, n:].view(world, b, H)
+    S_in = ops.fold_boundary_states(S_all, logP_all, rank) if rank > 0 else None
+    return S_in
+
+
 def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, ops=_cuda_ops, attention_mask=None):
     """The three-kernel core of ``Mamba2MixerPrefill.scan_core`` on this rank's shard of the sequence."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -64,8 +163,13 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
     w, bias = mixer.conv1d.weight.squeeze(1), mixer.conv1d.bias
     scan_kw = dict(dt_bias=mixer.f32_param("dt_bias"), dt_softplus=True, dt_limit=mixer.time_step_limit)
 
-    # 1. conv over the shard (zero halo) || halo all-gather, dt cumsum, conv of the first K-1 rows with the halo
+    # 1. conv over the shard (zero halo) || halo exchange, dt cumsum, conv of the first K-1 rows with the halo
     halo_send = xBC[:, L - (K - 1):, :].contiguous()                  # (b, K-1, conv_dim)
+    ex = _peer_exchange(group, dev, b, H, P, N, (b, K - 1, mixer.conv_dim), xBC.dtype) if (native and world <= 16) else None
+    parity = 0
+    if ex is not None:
+        parity = ex.step & 1
+        ex.step += 1
     if native:
         main, side = torch.cuda.current_stream(dev), _helper_stream(dev)
         xBC_c = torch.empty((b, L, mixer.conv_dim), dtype=xBC.dtype, device=dev)
@@ -82,17 +186,23 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
 
     head_rows = None
     with side_ctx:
-        halos = _all_gather_rows(halo_send, group)                    # (world, b, K-1, conv_dim)
+        if ex is not None:                                            # peer store into rank+1's buffer + signal
+            ex.send_halo(halo_send, parity)
+            halos = None
+        else:
+            halos = _all_gather_rows(halo_send, group)                # (world, b, K-1, conv_dim)
         if native:                                                    # needs dt only; scratch of the main stream
             x, B, C = views(xBC_c)
             ops.mamba_dt_cumsum_prepare(x, dt, A, B, mixer.chunk_size, workspace_stream=main, **scan_kw)
+        prev_halo = None
         if rank > 0:
-            conv_init = halos[rank - 1].transpose(1, 2).contiguous()  # (b, conv_dim, K-1)
+            prev_halo = ex.recv_halo(parity) if ex is not None else halos[rank - 1]
+            conv_init = prev_halo.transpose(1, 2).contiguous()        # (b, conv_dim, K-1)
             head_rows = ops.causal_conv1d_fn(x=xBC[:, :K - 1].transpose(1, 2), weight=w, bias=bias,
                                              initial_states=conv_init, activation=mixer.activation)
     if native:
         main.wait_stream(side)
-        for t in (halos, head_rows):
+        for t in (halos, head_rows, prev_halo if ex is None else None):
             if t is not None:
                 t.record_stream(main)
     else:
@@ -102,21 +212,21 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
         xBC_c[:, :K - 1].copy_(head_rows.transpose(1, 2))
     x, B, C = views(xBC_c)
 
-    # 2.-4. shard summary into one flat buffer, one all-gather, fold in place
+    # 2.-4. shard summary, exchange, fold
     n = b * H * P * N
-    flat = torch.empty(n + b * H, dtype=torch.float32 if native else xBC_c.dtype, device=dev)
-    S_r, logP_r = flat[:n].view(b, H, P, N), flat[n:].view(b, H)
-    if native:
-        ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, _reuse_dt_cumsum=True, out=(S_r, logP_r),
-                                      **scan_kw)
+    if ex is not None:
+        # summary straight into this rank's symmetric buffer; ONE device-side barrier; every rank then reads the summaries
+        # it needs from its peers inside the fold kernel (NVLink loads) -- no all-gather on the critical path
+        S_r, logP_r = ex.summary_views(parity)
+        ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, _reuse_dt_cumsum=True, out=(S_r, logP_r), **scan_kw)
+        ex.hdl.barrier(channel=parity)
+        if rank > 0:
+            sp, lp = ex.peer_ptrs(parity)
+            S_in = ops.fold_boundary_states_p2p(sp, lp, rank, (b, H, P, N), dev)
+        else:
+            S_in = None
     else:
-        s, lp = ops.mamba_chunk_state_summary(x, dt, A, B, mixer.chunk_size, **scan_kw)
-        S_r.copy_(s)
-        logP_r.copy_(lp)
-    gathered = _all_gather_rows(flat, group)                          # (world, n + b*H)
-    S_all = gathered[:, :n].view(world, b, H, P, N)
-    logP_all = gathered[:, n:].view(world, b, H)
-    S_in = ops.fold_boundary_states(S_all, logP_all, rank) if rank > 0 else None
+        S_in = _gathered_fold(ops, native, mixer, x, dt, A, B, scan_kw, b, H, P, N, n, xBC_c, dev, group, rank, world)
 
     # 5. full local scan from the folded entering state (dt/cumsum of step 1 is still in the op's scratch)
     reuse = {"_reuse_dt_cumsum": True} if native else {}
@@ -126,7 +236,7 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
         xt = xBC.transpose(1, 2)
         conv_states = nn.functional.pad(xt, (cache_params.conv_kernel_size - xt.shape[-1], 0))
         if L < K:   # left columns come from the previous shard, not zeros
-            conv_states[..., :K - L] = halos[rank - 1].transpose(1, 2)[..., L - K:] if rank > 0 else 0
+            conv_states[..., :K - L] = prev_halo.transpose(1, 2)[..., L - K:] if rank > 0 else 0
         cache_params.update_conv_state(layer_idx=mixer.layer_idx, new_conv_state=conv_states, cache_init=True)
         cache_params.update_ssm_state(layer_idx=mixer.layer_idx, new_ssm_state=ssm_state)
     y = ops.rmsnorm_fn(x=y.view(b, L, -1), weight=mixer.norm.weight, bias=None, z=gate,
