@@ -303,12 +303,12 @@ def run_ours(args):
         proj = mixer.in_proj(hs_dev)                                    # resident input of the hot path
     family = tv.ssd_kernel_family(torch.bfloat16, cfg.mamba_head_dim, cfg.ssm_state_size, cfg.chunk_size)
 
-    use_graph = not dist_on and not args.no_graph
+    use_graph = not args.no_graph
 
     def core():
         with torch.no_grad():
-            if dist_on:
-                return tv.sharded_scan_core(mixer, proj)[0]
+            if dist_on:     # sharded step; one CUDA graph replay per step when the peer (symmetric-memory) exchange is in use
+                return (tv.sharded_scan_core_graph(mixer, proj) if use_graph else tv.sharded_scan_core(mixer, proj))[0]
             if use_graph:       # the three kernels + the dt/cumsum pre-kernel replayed as ONE CUDA graph launch
                 return mixer.scan_core_graph(proj)
             return mixer.scan_core(proj)
@@ -438,8 +438,11 @@ def run_ours(args):
             line["parity"] = parity
         if sustained is not None:
             line["sustained"] = sustained
-        line["config"]["launch"] = ("one CUDA graph replay per step (conv, dt/cumsum, fused SSD, norm)" if use_graph
-                                    else "eager kernel launches")
+        line["config"]["launch"] = ("one CUDA graph replay per step" if use_graph else "eager kernel launches")
+        if dist_on:
+            from timeviper_b200 import sharded as _sh
+            line["config"]["boundary_exchange"] = ("symmetric memory: summary in place, one device barrier, fold reads peers "
+                                                   "over NVLink" if _sh._exchanges else "NCCL all-gather")
         print(json.dumps(line), flush=True)
     if dist_on:
         dist.destroy_process_group()

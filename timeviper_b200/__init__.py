@@ -12,11 +12,12 @@ from .mixer import Mamba2MixerPrefill, MambaRMSNormGated, patch_reference  # noq
 from .ops import (causal_conv1d_fn, causal_conv1d_update, fold_boundary_states, mamba_chunk_scan_combined,  # noqa: E402
                   mamba_chunk_state_summary, mamba_split_conv1d_scan_combined, rmsnorm_fn,
                   selective_state_update, ssd_kernel_family, launch_count)
-from .sharded import sharded_mixer_forward, sharded_prefill_from_host, sharded_scan_core  # noqa: E402
+from .sharded import (sharded_mixer_forward, sharded_prefill_from_host, sharded_scan_core,  # noqa: E402
+                      sharded_scan_core_graph)
 from .hybrid import HybridPrefillStack  # noqa: E402
 
 __all__ = ["Mamba2Config", "Mamba2MixerPrefill", "MambaRMSNormGated", "patch_reference", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_chunk_scan_combined", "mamba_split_conv1d_scan_combined",
            "rmsnorm_fn", "selective_state_update", "mamba_chunk_state_summary", "fold_boundary_states",
-           "ssd_kernel_family", "sharded_mixer_forward", "sharded_scan_core", "sharded_prefill_from_host",
+           "ssd_kernel_family", "sharded_mixer_forward", "sharded_scan_core", "sharded_prefill_from_host", "sharded_scan_core_graph",
            "HybridPrefillStack", "launch_count"]

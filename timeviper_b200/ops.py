@@ -154,6 +154,7 @@ def _workspace(nbytes, device, owner_stream=None):
     return ws
 
 
+force_simt_default = False  # tests: route every SSD call to the fp32 CUDA-core family (an fp32-accumulating reference on the GPU)
 simt_fallbacks = 0          # bf16 SSD calls served by the fp32 CUDA-core family (see _warn_simt_fallback)
 _simt_warned = set()
 
@@ -243,9 +244,9 @@ def _ssd_call(x, dt, A, B, C_, chunk_size, D, z, dt_bias, initial_states, dt_sof
         z_head_stride=0 if z is None else z.stride(2),
         d_has_hdim=int(D is not None and D.dim() == 2), dt_softplus=int(bool(dt_softplus)),
         dt_min=lo, dt_max=hi if math.isfinite(hi) else float("inf"), dtype=code, mode=mode,
-        force_simt=int(bool(force_simt)), reuse_dt_cumsum=int(bool(reuse_dt_cumsum)))
+        force_simt=int(bool(force_simt or force_simt_default)), reuse_dt_cumsum=int(bool(reuse_dt_cumsum)))
     lib = L.load()
-    if code == L.TV_BF16 and not force_simt and lib.tv_ssd_kernel_family(C.byref(p)) == 0:
+    if code == L.TV_BF16 and not (force_simt or force_simt_default) and lib.tv_ssd_kernel_family(C.byref(p)) == 0:
         _warn_simt_fallback(headdim, dstate, int(chunk_size))
     need = lib.tv_ssd_workspace_bytes(C.byref(p))
     ws = _workspace(need, dev, workspace_stream)

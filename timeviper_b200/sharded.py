@@ -76,8 +76,14 @@ class PeerExchange:
         self.halo = symm.empty(2 * self.halo_al, dtype=halo_dtype, device=device)
         self.halo_hdl = symm.rendezvous(self.halo, self.group)
         self.halo_shape, self.shape = tuple(halo_shape), (b, H, P, N)
-        self.step = 0
-        self.itemsize = self.halo.element_size()
+        self.last_parity = 1                          # the first step uses half 0
+        self.forced_parity = None                     # set while a CUDA graph of a given parity is captured
+
+    def next_parity(self):
+        """Half of the double buffers this step uses: always the other one than the previous step (eager or replayed)."""
+        p = self.forced_parity if self.forced_parity is not None else self.last_parity ^ 1
+        self.last_parity = p
+        return p
 
     def summary_views(self, parity):
         base = self.flat[parity * self.per_al: parity * self.per_al + self.per]
@@ -166,10 +172,7 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
     # 1. conv over the shard (zero halo) || halo exchange, dt cumsum, conv of the first K-1 rows with the halo
     halo_send = xBC[:, L - (K - 1):, :].contiguous()                  # (b, K-1, conv_dim)
     ex = _peer_exchange(group, dev, b, H, P, N, (b, K - 1, mixer.conv_dim), xBC.dtype) if (native and world <= 16) else None
-    parity = 0
-    if ex is not None:
-        parity = ex.step & 1
-        ex.step += 1
+    parity = ex.next_parity() if ex is not None else 0
     if native:
         main, side = torch.cuda.current_stream(dev), _helper_stream(dev)
         xBC_c = torch.empty((b, L, mixer.conv_dim), dtype=xBC.dtype, device=dev)
@@ -242,6 +245,46 @@ def sharded_scan_core(mixer, projected_states, group=None, cache_params=None, op
     y = ops.rmsnorm_fn(x=y.view(b, L, -1), weight=mixer.norm.weight, bias=None, z=gate,
                        eps=mixer.norm.variance_epsilon, group_size=mixer.norm.group_size, norm_before_gate=False)
     return y, ssm_state
+
+
+_sharded_graphs = {}
+
+
+@torch.no_grad()
+def sharded_scan_core_graph(mixer, projected_states, group=None):
+    """``sharded_scan_core`` replayed as ONE CUDA graph launch per step.  Possible because the boundary exchange is made of
+    ordinary kernels and peer copies (symmetric memory), not of NCCL calls.  Two graphs are captured, one per half of the
+    exchange's double buffers, and replayed alternately; the returned tensors are the graph's static outputs (overwritten
+    by the replay after next).  Falls back to eager launches where the peer exchange is unavailable."""
+    dev = projected_states.device
+    key = (projected_states.data_ptr(), tuple(projected_states.shape), projected_states.dtype, id(group), dev.index)
+    held = _sharded_graphs.get(key)
+    if held is None:
+        for _ in range(2):                                # both halves once, eagerly: allocations, lazy CUDA state
+            sharded_scan_core(mixer, projected_states, group=group)
+        ex = next((e for k, e in _exchanges.items() if k[1] == dev.index), None)
+        if ex is None:
+            held = _sharded_graphs[key] = {"graphs": None}
+        else:
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)
+            graphs = {}
+            for parity in (0, 1):
+                ex.forced_parity = parity
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    y, ssm = sharded_scan_core(mixer, projected_states, group=group)
+                graphs[parity] = (g, y, ssm)
+            ex.forced_parity = None
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)
+            held = _sharded_graphs[key] = {"graphs": graphs, "ex": ex}
+    if held["graphs"] is None:
+        return sharded_scan_core(mixer, projected_states, group=group)
+    parity = held["ex"].next_parity()
+    g, y, ssm = held["graphs"][parity]
+    g.replay()
+    return y, ssm
 
 
 def sharded_mixer_forward(mixer, hidden_states_shard, group=None, cache_params=None, ops=_cuda_ops):
