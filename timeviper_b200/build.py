@@ -30,7 +30,7 @@ def build(force=False, verbose=False, trace=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, *(["-DTV_ENABLE_TRACE"] if trace else []), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DTV_ENABLE_TRACE"] if trace else []), *(["-DTV_MBAR_DEBUG"] if os.environ.get("TV_MBAR_DEBUG") else []), "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, pr in procs:

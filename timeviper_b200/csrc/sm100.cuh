@@ -52,12 +52,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
   return ok != 0;
 }
-// Bounded spin: a protocol bug must not hang the GPU box (a hang is a strike); report and trap instead.
+// Non-blocking probe (try_wait may suspend the thread for a hardware time limit while the phase is pending, which is what
+// a waiter wants and what a thread that POLLS several barriers must avoid).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must not hang the GPU box (a hang is a strike); trap instead.  The diagnostic printf is
+// compiled in only with -DTV_MBAR_DEBUG: a real function call inside a kernel that re-partitions its registers with
+// setmaxnreg makes ptxas compile EVERY role to the smallest budget (measured: the whole fused SSD kernel at 40 registers
+// with 1.5 KB of spills), so the normal build has no call on this path.
+#ifdef TV_MBAR_DEBUG
 __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
   printf("mbar_wait timeout: block (%d,%d) thread %d barrier smem+0x%x parity %u\n", blockIdx.x, blockIdx.y,
          threadIdx.x, bar_addr, parity);
   __trap();
 }
+#else
+__device__ __forceinline__ void mbar_timeout(uint32_t, uint32_t) { __trap(); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -119,6 +139,8 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
 __device__ __forceinline__ void bulk_prefetch(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+// L2 prefetch of the 128-byte line that holds p (plain LSU instruction, no TMA involved)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 1-D bulk copy global -> shared (bytes multiple of 16, both 16-byte aligned)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -3,25 +3,33 @@
 //
 // Replaces the five mamba_ssm Triton kernels behind mamba_chunk_scan_combined
 // (visualize/nano/my_ssd_combined.py:795-826) with ONE persistent kernel.  One CTA owns one (batch, head)
-// and walks the chunks in order with the 128x80 fp32 running state resident in TMEM, so the per-chunk
-// states / C.B^T tiles that the reference materialises in HBM (~123 KB per token) never leave the SM:
-// HBM traffic is the algorithmic 45,312 B/token (x, B, C, dt in; y out).
+// and walks the chunks in order; the per-chunk states / C.B^T tiles that the reference materialises in HBM
+// (~123 KB per token) never leave the SM: HBM traffic is the algorithmic 45,312 B/token (x, B, C, dt in; y out).
 //
 // Per chunk c (m, k: tokens in the chunk; n: state; p: head dim), with cs = inclusive cumsum of dt*A:
-//   G: CB[m,k]   = sum_n C[m,n] B[k,n]                                   tcgen05 SS, 128x128x128 -> TMEM
-//      M[m,k]    = CB[m,k] * exp(cs_m - cs_k) * dt_k  (k <= m)           WG_A: TMEM -> regs -> bf16 -> TMEM
+//   G: CB[m,k]   = sum_n C[m,n] B[k,n]                                   tcgen05 SS, 128x128x128 -> TMEM (2 buffers)
+//      M[m,k]    = CB[m,k] * exp(cs_m - cs_k) * dt_k  (k <= m)           WG_A + helper: TMEM -> regs -> bf16 -> TMEM,
+//                                                                         IN PLACE over the first 64 columns of CB
 //   D: Yd[m,p]   = sum_k M[m,k] x[k,p]                                   tcgen05 TS (A = M in TMEM), N = 80
 //   O: Yo[m,p]   = sum_n C[m,n] S_c[n,p]          (S_c = state entering the chunk, bf16 copy in smem)
-//   S: S_{c+1}   = exp(cs_last) * S_c + sum_k B[k,n] * (dt_k exp(cs_last - cs_k) x[k,p])
-//                  decay: WG_B TMEM -> regs -> TMEM; the sum: tcgen05 SS accumulating onto it
+//   S: dS[n,p]   = sum_k B[k,n] * (dt_k exp(cs_last - cs_k) x[k,p])      tcgen05 SS into a FRESH accumulator
+//      S_{c+1}   = exp(cs_last) * S_c + dS                               WG_S: the running state lives in REGISTERS
 //      y[m,p]    = Yd + exp(cs_m) * Yo + D * x[m,p]   [* silu(z)]         WG_C: TMEM -> regs -> bf16 tile staged in the
 //                                                                         dead x stage -> TMA tensor store
 // Decay, mask and cumsum stay in fp32 registers; only the four contractions touch the tensor cores.
 //
-// Warp roles (576 threads): warps 0-3 = WG_A and 4-7 = WG_H (build M), warps 8-11 = WG_B (x scaling, state decay,
-// bf16 state copy), warps 12-15 = WG_C (epilogue), warp 16 = TMA producer, warp 17 =
-// MMA issuer + TMEM owner.  B, C and x tiles have their own full/empty mbarriers; B and C are released as soon as
-// their last MMA has completed, the x stage once TMA has read the y tile the epilogue staged in it.  Tensor-pipe order per iteration is S(c), O(c), D(c), G(c+1).
+// Round-2 dataflow (why it looks like this: profiles/r02_ssd_restructure.md).  The round-1 kernel kept the state in a
+// TMEM accumulator that the S MMA accumulated onto, so every chunk paid MMA -> commit -> TMEM load / decay / store ->
+// MMA as a serial chain, and one in-order issuing thread coupled that chain to the C.B^T -> M -> D chain.  Here
+//   * the S MMA never accumulates across chunks: the recurrence is 80 FMAs per thread in WG_S's registers, everything
+//     else is feed-forward;
+//   * C.B^T is double-buffered in TMEM and M overwrites it in place, so G(c+1) / M(c+1) run a chunk ahead;
+//   * two issuing threads: (G, D) and (S, O);  the TMA producer polls its three rings instead of waiting in order;
+//   * register budgets per role via setmaxnreg (WG_S holds the 128x80 fp32 state: 80 registers per thread).
+//
+// Warp roles (640 threads): warps 0-3 = WG_A (diagonal M blocks, block 2 of the last row quarter), warps 4-7 = WG_X
+// (x scaling for the S MMA + the off-diagonal M blocks 0/1), warps 8-11 = WG_S (state), warps 12-15 = WG_C (epilogue),
+// warp 16 = TMA producer, warp 17 = issuer of G / D + TMEM owner, warp 18 = issuer of S / O.
 #include "common.cuh"
 #include "sm100.cuh"
 #include "ssd.h"
@@ -36,30 +44,42 @@ using namespace sm100;
 
 namespace tc {
 constexpr int Q = 128, P = 80, N = 128;
-// L2 prefetch ahead of the smem loads, bitmask: 1 = x tiles, 2 = cs/dt rows, 4 = B/C tiles (group leader).  It paid
-// off in the first versions of the kernel; measured on the current one at 128K tokens it COSTS 1-5 % in every
-// combination (2.08 ms without, 2.18 / 2.10 / 2.09 / 2.16 / 2.20 ms with 1 / 2 / 4 / 6 / 7), so it is off.
-#ifndef TV_SSD_L2_PREFETCH
-#define TV_SSD_L2_PREFETCH 0
+// L2 prefetch distance of the TMA producer (chunks ahead of the shared-memory loads; 0 = off).  x / cs / dt are prefetched
+// by every CTA, the B / C tiles (shared by the heads of a group) by the group's first head only.
+#ifndef TV_SSD_PF
+#define TV_SSD_PF 0
 #endif
-constexpr int THREADS = 576;                      // WG_A, WG_H, WG_B, WG_C (4 warps each) + producer + MMA issuer
-constexpr int W_A = 0, W_H = 4, W_B = 8, W_C = 12, W_PROD = 16, W_MMA = 17;   // first warp of each role
+constexpr int THREADS = 640;
+constexpr int W_A = 0, W_X = 4, W_S = 8, W_C = 12, W_PROD = 16, W_MMA = 17, W_PF = 18;   // first warp of each role
+// Registers per thread after setmaxnreg.  The pool is what the CTA was LAUNCHED with (640 threads x 96 registers, the
+// most __launch_bounds__(640) allows), not the SM's register file: the five warpgroups must sum to 5 x 96 = 480.
+constexpr int REG_LAUNCH = 96;
+constexpr int REG_A = 104, REG_X = 72, REG_S = 136, REG_C = 104, REG_MISC = 64;
+static_assert(REG_A + REG_X + REG_S + REG_C + REG_MISC <= 5 * REG_LAUNCH, "register pool of the CTA");
+template <int R> __device__ __forceinline__ void reg_set() {      // executed by all four warps of a warpgroup
+  if (R > REG_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+  if (R < REG_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+}
 constexpr uint32_t TILE_BC = Q * N * 2;          // 32768: two 16 KB halves (n 0..63 | 64..127), SW128
 constexpr uint32_t TILE_X = 5 * 4096;            // 20480: five 16-wide p atoms, SW32
 constexpr uint32_t XSTAGE = TILE_X + 1024;       // x tile | cs[128] f32 | dt[128] f32
 constexpr uint32_t OFF_B = 0, OFF_C = 2 * TILE_BC, OFF_X = 4 * TILE_BC;          // two buffers of each
-constexpr uint32_t OFF_XS = OFF_X + 2 * XSTAGE, OFF_S = OFF_XS + TILE_X, OFF_F = OFF_S + TILE_X;
-constexpr uint32_t FBUF = 2560;                  // per buffer: F[128] | V1[128] | V2[128] | V3[128] | U[128] (fp32)
-constexpr uint32_t OFF_D = OFF_F + 2 * FBUF;     // 80 floats (D row), padded to 512
+constexpr uint32_t OFF_XS = OFF_X + 2 * XSTAGE, OFF_S = OFF_XS + TILE_X, OFF_Y = OFF_S + TILE_X;
+constexpr uint32_t YSTG = 3 * 1024;              // per epilogue warp: three 32-row x 16-column SW32 atoms of staged y
+constexpr uint32_t OFF_SCR = OFF_Y + 4 * YSTG;
+constexpr uint32_t SCR = 512;                    // per-warp fp32 scratch of the 4 M-building warps (decay factors)
+constexpr uint32_t OFF_D = OFF_SCR + 4 * SCR;    // 80 floats (D row), padded to 512
 constexpr uint32_t OFF_BAR = OFF_D + 512;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;   // + barriers + alignment slack
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
 static_assert(OFF_XS % 1024 == 0 && OFF_S % 1024 == 0 && XSTAGE % 256 == 0, "tile alignment");
 static_assert(SMEM_BYTES <= kMaxDynSmem, "smem budget");
-// TMEM columns
-constexpr uint32_t T_CB = 0, T_M0 = 128, T_M1 = 192, T_YD = 256, T_YO = 336, T_ST = 416;   // M: 64 cols of packed bf16
+// TMEM columns: C.B^T / M (two buffers; M = 64 columns of packed bf16 written over columns 0..63), Yd, Yo, dS
+constexpr uint32_t T_CB0 = 0, T_CB1 = 128, T_YD = 256, T_YO = 336, T_DS = 416;
 
 enum Bar { FULLB0 = 0, FULLB1, EMPTYB0, EMPTYB1, FULLC0, FULLC1, EMPTYC0, EMPTYC1, FULLX0, FULLX1, EMPTYX0, EMPTYX1,
-           CBFULL, CBEMPTY, MFULL0, MFULL1, FRDY0, FRDY1, XSFULL, SDECAY, SFULL, STDONE, YOFFDONE, YFULL, YEMPTY, NBAR };
+           CBFULL0, CBFULL1, MFULL0, MFULL1, XSFULL, STDONE, DSFREE, SFULL, YOFULL, YDFULL, YDFREE, YOFREE,
+           NBAR };
+static_assert(NBAR * 8 + 8 <= 512, "barrier area");
 
 struct Maps { CUtensorMap x, b, c, y; };
 
@@ -69,6 +89,8 @@ struct Args {
   __nv_bfloat16* out; float* fin; float* logdecay;
   int L, H, G, nchunks, d_has_hdim;
   int64_t zbs, zss, zhs;
+  const __nv_bfloat16 *xp, *bp, *cp;               // raw pointers / element strides of x, B, C: L2 prefetch warp only
+  int64_t xbs, xss, xhs, bbs, bss, bgs, cbs, css, cgs;
   long long* trace;                                // optional: per-chunk clock64 stamps of CTA (0,0), 16 per chunk
   int ablate;                                      // profiling only (TV_ENABLE_TRACE builds): bitmask of work to skip
 };
@@ -81,10 +103,10 @@ struct Args {
 #else
 #define TV_TRACE(ev, c) do { } while (0)
 #endif
-// Ablation switches (profiling builds only): tools/ablate_ssd.py times the kernel with parts of the work skipped
-// to find the critical path; in normal builds TV_ABLATE() is the constant 0 and the branches vanish.
-#ifdef TV_ENABLE_TRACE
-#define TV_ABLATE(bit) ((a.ablate >> (bit)) & 1)
+// Ablation switches (variant builds only, tools/build_variants.py): the kernel with parts of the work skipped, to find
+// the critical path; in normal builds TV_ABLATE() is the constant 0 and the branches vanish.
+#if defined(TV_ABL)      // compile-time mask (tools/build_variants.py): no register or branch cost, unlike the trace build
+#define TV_ABLATE(bit) (((TV_ABL) >> (bit)) & 1)
 #else
 #define TV_ABLATE(bit) 0
 #endif
@@ -93,18 +115,13 @@ __device__ __forceinline__ uint32_t off_sw32(int r, int q) {  // row r, 16-byte 
 }
 }  // namespace tc
 
-// Tensor-pipe order per iteration c:  S(c)  O(c)  D(c)  G(c+1).
-//   S first: it is the loop-carried dependency (state);  its B tile is released right after it.
-//   O second: reads the bf16 copy of S_c, so that copy (single smem buffer) is free again by the time WG_B has the
-//             next entering state; releases the C tile.
-//   D third: M(c) was built during the previous iteration; completes y of chunk c and releases the x stage.
-//   G(c+1) last: look-ahead C.B^T; WG_A builds M(c+1) while S(c+1) and O(c+1) run.
-// One 32x32 block of M for this warp's 32 rows: M[m,k] = CB[m,k] * 2^(Em + F_k), masked to k <= m on the diagonal
-// block.  Written stage by stage (TMEM load, 32 exponent arguments, 32 MUFU.EX2, 32 FMUL, 16 packs, TMEM store) so
-// that the exp2 stream is issue-bound on the XU pipe (8 cycles per warp instruction) instead of latency-bound.
+// One diagonal 32x32 block of M for this warp's 32 rows: M[m,k] = CB[m,k] * 2^(Em + F_k), masked to k <= m.  The packed
+// bf16 result stays in registers (the caller stores it once the columns it overwrites have been read by everybody).
+// Written stage by stage (TMEM load, 32 exponent arguments, 32 MUFU.EX2, 32 FMUL, 16 packs) so that the exp2 stream is
+// issue-bound on the XU pipe (8 cycles per warp instruction) instead of latency-bound.
 template <bool DFOLD>
-__device__ __forceinline__ void m_block(uint32_t t_src, uint32_t t_dst, const float* __restrict__ sFk, float Em,
-                                        int lane, float Dh, bool diag) {
+__device__ __forceinline__ void m_diag(uint32_t t_src, uint32_t (&pk)[16], const float* __restrict__ sFk, float Em,
+                                       int lane, float Dh) {
   uint32_t r[32];
   tmem_ld32(t_src, r);
   float2 e[16];                                  // packed pairs: FADD2 / FMUL2 halve the FP issue slots
@@ -118,48 +135,49 @@ __device__ __forceinline__ void m_block(uint32_t t_src, uint32_t t_dst, const fl
 #pragma unroll
   for (int j = 0; j < 16; ++j) e[j] = make_float2(ex2_approx(e[j].x), ex2_approx(e[j].y));
   tmem_ld_wait();
-  uint32_t pk[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float2 v = __fmul2_rn(e[j], make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
-    if (diag && 2 * j > lane) v.x = 0.f;                   // causal mask (diagonal block only)
-    if (diag && 2 * j + 1 > lane) v.y = 0.f;
-    if (DFOLD && diag && 2 * j == lane) v.x += Dh;         // D skip folded into the diagonal
-    if (DFOLD && diag && 2 * j + 1 == lane) v.y += Dh;
+    if (2 * j > lane) v.x = 0.f;                   // causal mask
+    if (2 * j + 1 > lane) v.y = 0.f;
+    if (DFOLD && 2 * j == lane) v.x += Dh;         // D skip folded into the diagonal
+    if (DFOLD && 2 * j + 1 == lane) v.y += Dh;
     pk[j] = pack_bf16x2(v.x, v.y);
   }
-  tmem_st16(t_dst, pk);
 }
 
 // Off-diagonal 32x32 block (every k of the block precedes every row of this warp): the decay factorises without
 // overflow around ref = cs at the last token before the warp's rows,
 //   exp(cs_m - cs_k) dt_k = u_m * v_k,   u_m = exp(cs_m - ref) <= 1,   v_k = dt_k exp(ref - cs_k) <= dt_k,
-// so the block costs two FMULs per element and NO transcendental (u_m: one exp per row, v_k: <= 3 per column per chunk).
-__device__ __forceinline__ void m_block_offdiag(uint32_t t_src, uint32_t t_dst, const float* __restrict__ sVk, float um) {
+// so the block costs two FMULs per element and NO transcendental (u_m: one exp per row, v_k: one per column).
+__device__ __forceinline__ void m_offdiag(uint32_t t_src, uint32_t (&pk)[16], const float* __restrict__ sVk, float um) {
   uint32_t r[32];
   tmem_ld32(t_src, r);
-  float2 e[16];
   const float2 um2 = make_float2(um, um);
+  tmem_ld_wait();
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
     const float4 v4 = *reinterpret_cast<const float4*>(sVk + 2 * j);
-    e[j] = __fmul2_rn(make_float2(v4.x, v4.y), um2);
-    e[j + 1] = __fmul2_rn(make_float2(v4.z, v4.w), um2);
+    const float2 e0 = __fmul2_rn(make_float2(v4.x, v4.y), um2), e1 = __fmul2_rn(make_float2(v4.z, v4.w), um2);
+    const float2 a0 = __fmul2_rn(e0, make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+    const float2 a1 = __fmul2_rn(e1, make_float2(__uint_as_float(r[2 * j + 2]), __uint_as_float(r[2 * j + 3])));
+    pk[j] = pack_bf16x2(a0.x, a0.y);
+    pk[j + 1] = pack_bf16x2(a1.x, a1.y);
   }
-  tmem_ld_wait();
-  uint32_t pk[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float2 v = __fmul2_rn(e[j], make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
-    pk[j] = pack_bf16x2(v.x, v.y);
-  }
-  tmem_st16(t_dst, pk);
 }
 
 // DFOLD: D is a per-head scalar and is added to the diagonal of M (bf16 A operand), so that Yd = (M + D I) x and
 // the epilogue never touches x.  For bf16 parameters D*x is exact in the fp32 accumulator; the only extra rounding
 // is bf16(M_mm + D), of the order of the bf16 rounding of y itself.  D of shape (H, P) takes the explicit path.
-template <bool FULL, bool HAS_Z, bool DFOLD>
+//
+// mbarrier phases: a barrier that is used once per chunk is never more than one phase ahead of any of its waiters
+// (every producer of phase c+1 depends, directly or not, on each waiter of phase c having passed its wait); the
+// per-buffer barriers (..0 / ..1) advance once per two chunks under the same rule.  The orders that make this true:
+//   issuer SO:  S(c) before O(c)   -- YOFULL(c) therefore also says that xs(c) was consumed, i.e. WG_X has finished
+//                                     reading the raw x tile of chunk c, which the epilogue then overwrites with y(c);
+//   issuer GD:  G(c+1) before D(c) -- G(c+1) waits for D(c-1) (YDFULL), whose A operand M(c-1) lives in the buffer it
+//                                     overwrites.
+template <bool HAS_Z, bool DFOLD>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   using namespace tc;
@@ -167,23 +185,25 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBAR * 8);
-  const int warp = threadIdx.x >> 5;
+  volatile int* progress = reinterpret_cast<volatile int*>(smem + OFF_BAR + NBAR * 8 + 8);   // x tiles issued by the producer
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
   const int hpg = a.H / a.G;
   const int g = h / hpg;
   const int n = a.nchunks;
+  constexpr float LOG2E = 1.4426950408889634f;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[FULLB0 + i], 1); mbar_init(&bars[FULLC0 + i], 1); mbar_init(&bars[FULLX0 + i], 1);
-      mbar_init(&bars[EMPTYB0 + i], 1); mbar_init(&bars[EMPTYC0 + i], 1);
-      mbar_init(&bars[EMPTYX0 + i], FULL ? 9 : 4);   // one lane per WG_A and WG_B warp + the epilogue's y-store thread
-      mbar_init(&bars[MFULL0 + i], 8); mbar_init(&bars[FRDY0 + i], 4);
+      mbar_init(&bars[EMPTYB0 + i], 2); mbar_init(&bars[EMPTYC0 + i], 2);   // one commit from each issuer
+      mbar_init(&bars[EMPTYX0 + i], DFOLD ? 9 : 13);   // one lane per WG_A and WG_X warp + the D commit (+ WG_C: explicit D*x)
+      mbar_init(&bars[CBFULL0 + i], 1);
+      mbar_init(&bars[MFULL0 + i], 4);
     }
-    mbar_init(&bars[CBFULL], 1); mbar_init(&bars[CBEMPTY], 8);
-    mbar_init(&bars[XSFULL], 4); mbar_init(&bars[SDECAY], 4); mbar_init(&bars[SFULL], 4);
-    mbar_init(&bars[STDONE], 1); mbar_init(&bars[YOFFDONE], 1); mbar_init(&bars[YFULL], 1);
-    mbar_init(&bars[YEMPTY], 4);
+    mbar_init(&bars[XSFULL], 4); mbar_init(&bars[STDONE], 1); mbar_init(&bars[DSFREE], 4); mbar_init(&bars[SFULL], 4);
+    mbar_init(&bars[YOFULL], 1); mbar_init(&bars[YDFULL], 1); mbar_init(&bars[YDFREE], 4); mbar_init(&bars[YOFREE], 4);
+    *progress = 0;
     fence_mbar_init();
   }
   if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
@@ -197,223 +217,265 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   const uint32_t tmem = *tmem_slot;
   const int64_t row0 = ((int64_t)b * n) * a.H + h;     // (b, c, h) row of dt_act / cs is row0 + c*H
 
-  if (warp == W_PROD) {
-    // =========================== TMA producer ===========================
-    if (elect_one()) {
-      prefetch_tmap(&maps.x); prefetch_tmap(&maps.b);
-      if (FULL) { prefetch_tmap(&maps.c); prefetch_tmap(&maps.y); }
-      const bool group_leader = (h % hpg) == 0;      // one CTA per group warms L2 with the shared B / C tiles
-      auto l2_prefetch = [&](int c) {
-        const int t0 = c * Q;
-        if (TV_SSD_L2_PREFETCH & 1) {
-#pragma unroll
-          for (int i = 0; i < 5; ++i) tma_prefetch_4d(&maps.x, 16 * i, h, t0, b);
-        }
-        if (TV_SSD_L2_PREFETCH & 2) {
-          bulk_prefetch(a.cs + (row0 + (int64_t)c * a.H) * Q, 512);
-          bulk_prefetch(a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512);
-        }
-        if ((TV_SSD_L2_PREFETCH & 4) && group_leader) {
-          tma_prefetch_4d(&maps.b, 0, g, t0, b); tma_prefetch_4d(&maps.b, 64, g, t0, b);
-          if (FULL) { tma_prefetch_4d(&maps.c, 0, g, t0, b); tma_prefetch_4d(&maps.c, 64, g, t0, b); }
-        }
-      };
-      constexpr int PF = 3;                         // L2 prefetch distance (chunks ahead of the smem loads)
-      if (TV_SSD_L2_PREFETCH) for (int c = 1; c < PF && c < n; ++c) l2_prefetch(c);
-      for (int c = 0; c < n; ++c) {
-        const int s = c & 1, u = c >> 1;
-        const int t0 = c * Q;
-        if (TV_SSD_L2_PREFETCH && c + PF < n && !TV_ABLATE(10)) l2_prefetch(c + PF);
-        if (c >= 2) mbar_wait(&bars[EMPTYB0 + s], (u - 1) & 1);
-        TV_TRACE(0, c);
+  if (warp >= W_PROD) {
+    reg_set<REG_MISC>();
+    if (warp == W_PROD) {
+      // =========================== TMA producer: three rings, polled ===========================
+      if (elect_one()) {
+        prefetch_tmap(&maps.x); prefetch_tmap(&maps.b); prefetch_tmap(&maps.c); prefetch_tmap(&maps.y);
+        int cb = 0, cc = 0, cx = 0;
+        while (cb < n || cc < n || cx < n) {
+          if (cx < n) {
+            const int s = cx & 1, u = cx >> 1;
+            if (cx < 2 || mbar_test_wait(&bars[EMPTYX0 + s], (u - 1) & 1)) {
+              TV_TRACE(0, cx);
 #ifdef TV_ENABLE_TRACE
-        if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
-          unsigned long long gt;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-          a.trace[(int64_t)c * 16 + 15] = (long long)gt;
-        }
+              if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+                unsigned long long gt;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                a.trace[(int64_t)cx * 16 + 15] = (long long)gt;
+              }
 #endif
-        if (TV_ABLATE(9)) mbar_arrive(&bars[FULLB0 + s]); else {
-        mbar_arrive_expect_tx(&bars[FULLB0 + s], TILE_BC);
-        tma_load_4d(smem + OFF_B + s * TILE_BC, &maps.b, &bars[FULLB0 + s], 0, g, t0, b);
-        tma_load_4d(smem + OFF_B + s * TILE_BC + 16384, &maps.b, &bars[FULLB0 + s], 64, g, t0, b);
-        }
-        if (FULL) {
-          if (c >= 2) mbar_wait(&bars[EMPTYC0 + s], (u - 1) & 1);
-          if (TV_ABLATE(9)) mbar_arrive(&bars[FULLC0 + s]); else {
-          mbar_arrive_expect_tx(&bars[FULLC0 + s], TILE_BC);
-          tma_load_4d(smem + OFF_C + s * TILE_BC, &maps.c, &bars[FULLC0 + s], 0, g, t0, b);
-          tma_load_4d(smem + OFF_C + s * TILE_BC + 16384, &maps.c, &bars[FULLC0 + s], 64, g, t0, b);
-          }
-        }
-        if (c >= 2) mbar_wait(&bars[EMPTYX0 + s], (u - 1) & 1);
-        TV_TRACE(14, c);
-        uint8_t* xs_ = smem + OFF_X + s * XSTAGE;
-        mbar_arrive_expect_tx(&bars[FULLX0 + s], TV_ABLATE(8) ? 1024 : XSTAGE);
-        if (!TV_ABLATE(8))
+              uint8_t* xs_ = smem + OFF_X + s * XSTAGE;
+              const int t0 = cx * Q;
+              mbar_arrive_expect_tx(&bars[FULLX0 + s], TV_ABLATE(8) ? 1024 : (TV_ABLATE(14) ? 2 * 4096 + 1024 : XSTAGE));
+              if (!TV_ABLATE(8))
 #pragma unroll
-        for (int i = 0; i < 5; ++i) tma_load_4d(xs_ + i * 4096, &maps.x, &bars[FULLX0 + s], 16 * i, h, t0, b);
-        bulk_load(xs_ + TILE_X, a.cs + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULLX0 + s]);
-        bulk_load(xs_ + TILE_X + 512, a.dt_act + (row0 + (int64_t)c * a.H) * Q, 512, &bars[FULLX0 + s]);
-      }
-    }
-  } else if (warp == W_MMA) {
-    // =========================== MMA issuer ===========================
-    if (elect_one()) {
-      constexpr uint32_t ID_CB = umma_idesc_bf16(128, 128, false, false);
-      constexpr uint32_t ID_Y = umma_idesc_bf16(128, P, false, true);
-      constexpr uint32_t ID_ST = umma_idesc_bf16(128, P, true, true);
-      const uint32_t sbase = smem_u32(smem);
-      // descriptor templates; per-MMA offsets are added to the 14-bit start-address field (units of 16 bytes)
-      const uint64_t dB_k = umma_smem_desc(sbase + OFF_B, 16, 1024, SWZ_128B);        // B as K-major operand (G)
-      const uint64_t dB_mn = umma_smem_desc(sbase + OFF_B, 16384, 1024, SWZ_128B);    // B as MN-major A operand (S)
-      const uint64_t dC_k = umma_smem_desc(sbase + OFF_C, 16, 1024, SWZ_128B);
-      const uint64_t dX = umma_smem_desc(sbase + OFF_X, 4096, 256, SWZ_32B);
-      const uint64_t dXS = umma_smem_desc(sbase + OFF_XS, 4096, 256, SWZ_32B);
-      const uint64_t dS = umma_smem_desc(sbase + OFF_S, 4096, 256, SWZ_32B);
-      // The issue loops are fully unrolled with compile-time descriptor offsets: a rolled loop costs ~110 cycles per
-      // MMA on the single issuing thread (descriptor arithmetic + R2UR), which made issue the bottleneck.
-      auto issue_cb = [&](int c) {   // G(c): CB = C . B^T
-        const int s = c & 1, u = c >> 1;
-        mbar_wait(&bars[FULLB0 + s], u & 1);
-        mbar_wait(&bars[FULLC0 + s], u & 1);
-        if (c > 0) mbar_wait(&bars[CBEMPTY], (c - 1) & 1);     // WG_A / WG_H have read CB(c-1) out of the single buffer
-        tc_fence_after();
-        TV_TRACE(1, c);
-        const uint32_t so = (uint32_t)(s * (TILE_BC >> 4));
-        const uint64_t dc = umma_desc_advance(dC_k, so), db = umma_desc_advance(dB_k, so);
-        if (!TV_ABLATE(4))
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
-          umma_ss(tmem + T_CB, umma_desc_advance(dc, o), umma_desc_advance(db, o), ID_CB, j > 0);
-        }
-        umma_commit(&bars[CBFULL]);
-      };
-      if (FULL) issue_cb(0);
-#pragma unroll 1
-      for (int c = 0; c < n; ++c) {
-        const int s = c & 1, u = c >> 1;
-        const uint32_t so = (uint32_t)(s * (TILE_BC >> 4));
-        // ---- S(c): state += B^T . xs
-        mbar_wait(&bars[FULLB0 + s], u & 1);
-        mbar_wait(&bars[SDECAY], c & 1);
-        mbar_wait(&bars[XSFULL], c & 1);
-        tc_fence_after();
-        TV_TRACE(2, c);
-        {
-          const uint64_t db = umma_desc_advance(dB_mn, so);
-          if (!TV_ABLATE(7))
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_ss(tmem + T_ST, umma_desc_advance(db, j * 128), umma_desc_advance(dXS, j * 32), ID_ST, 1u);
-        }
-        umma_commit(&bars[STDONE]);
-        umma_commit(&bars[EMPTYB0 + s]);
-        if (FULL) {
-          // ---- O(c): Yo = C . S_c
-          mbar_wait(&bars[FULLC0 + s], u & 1);
-          mbar_wait(&bars[SFULL], c & 1);
-          if (c > 0) mbar_wait(&bars[YEMPTY], (c - 1) & 1);
-          tc_fence_after();
-          TV_TRACE(3, c);
-          {
-            const uint64_t dc = umma_desc_advance(dC_k, so);
-            if (!TV_ABLATE(5))
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
-              umma_ss(tmem + T_YO, umma_desc_advance(dc, o), umma_desc_advance(dS, j * 32), ID_Y, j > 0);
+              for (int i = 0; i < (TV_ABLATE(14) ? 2 : 5); ++i) tma_load_4d(xs_ + i * 4096, &maps.x, &bars[FULLX0 + s], 16 * i, h, t0, b);
+              bulk_load(xs_ + TILE_X, a.cs + (row0 + (int64_t)cx * a.H) * Q, 512, &bars[FULLX0 + s]);
+              bulk_load(xs_ + TILE_X + 512, a.dt_act + (row0 + (int64_t)cx * a.H) * Q, 512, &bars[FULLX0 + s]);
+              ++cx;
+              *progress = cx;
             }
           }
-          umma_commit(&bars[YOFFDONE]);
-          umma_commit(&bars[EMPTYC0 + s]);
-          // ---- D(c): Yd = M . x   (A = M(c), packed bf16, in its own TMEM buffer)
-          mbar_wait(&bars[FULLX0 + s], u & 1);
-          mbar_wait(&bars[MFULL0 + s], u & 1);
-          tc_fence_after();
-          TV_TRACE(4, c);
-          {
-            const uint64_t dx = umma_desc_advance(dX, (uint32_t)(s * (XSTAGE >> 4)));
-            const uint32_t tmA = tmem + (s ? T_M1 : T_M0);
-            if (!TV_ABLATE(6))
-#pragma unroll
-            for (int j = 0; j < 8; ++j) umma_ts(tmem + T_YD, tmA + j * 8, umma_desc_advance(dx, j * 32), ID_Y, j > 0);
+          if (cb < n) {
+            const int s = cb & 1, u = cb >> 1;
+            if (cb < 2 || mbar_test_wait(&bars[EMPTYB0 + s], (u - 1) & 1)) {
+              const int t0 = cb * Q;
+              if (TV_ABLATE(9)) mbar_arrive(&bars[FULLB0 + s]); else {
+              mbar_arrive_expect_tx(&bars[FULLB0 + s], TILE_BC);
+              tma_load_4d(smem + OFF_B + s * TILE_BC, &maps.b, &bars[FULLB0 + s], 0, g, t0, b);
+              tma_load_4d(smem + OFF_B + s * TILE_BC + 16384, &maps.b, &bars[FULLB0 + s], 64, g, t0, b);
+              }
+              ++cb;
+            }
           }
-          umma_commit(&bars[YFULL]);                 // the x stage is released by the epilogue (it stages y in it)
-          // ---- G(c+1)
-          if (c + 1 < n) issue_cb(c + 1);
+          if (cc < n) {
+            const int s = cc & 1, u = cc >> 1;
+            if (cc < 2 || mbar_test_wait(&bars[EMPTYC0 + s], (u - 1) & 1)) {
+              const int t0 = cc * Q;
+              if (TV_ABLATE(9)) mbar_arrive(&bars[FULLC0 + s]); else {
+              mbar_arrive_expect_tx(&bars[FULLC0 + s], TILE_BC);
+              tma_load_4d(smem + OFF_C + s * TILE_BC, &maps.c, &bars[FULLC0 + s], 0, g, t0, b);
+              tma_load_4d(smem + OFF_C + s * TILE_BC + 16384, &maps.c, &bars[FULLC0 + s], 64, g, t0, b);
+              }
+              ++cc;
+            }
+          }
         }
       }
-    }
-  } else if (warp < W_B) {
-    // =========================== WG_A + WG_H: M = CB (.) decay, TMEM -> registers -> TMEM ===========================
-    // Row quarter q (TMEM lanes 32q..32q+31, i.e. SMSP q) owns q+1 blocks of 32 columns.  WG_A's warp q takes the
-    // diagonal block (the only one that needs exponentials) and block 2 of quarter 3; WG_H's warp q takes blocks
-    // 0 and 1 of quarters 2 and 3 and block 0 of quarter 1.  M(c) has its own TMEM buffer, so nothing is overwritten in
-    // place and the blocks above the diagonal are zeroed once, before the first chunk.
-    if (FULL) {
-      const bool helper = warp >= W_H;
-      const int q = warp & 3, lane = threadIdx.x & 31;
-      const int m = q * 32 + lane;
-      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-      constexpr float LOG2E = 1.4426950408889634f;
-      const float Dh = (DFOLD && a.D != nullptr) ? a.D[h] : 0.f;
-      if (!helper) {                               // zero both M buffers once (columns above the diagonal stay zero)
-        uint32_t zz[16];
+    } else if (warp == W_PF) {
+      // =========================== L2 prefetch warp ===========================
+      // Plain prefetch.global.L2 of the lines of chunk c + TV_SSD_PF, paced by the producer's progress counter, so that the
+      // TMA loads (whose latency sits in every ring of this kernel) hit L2.  Prefetches issued THROUGH the TMA unit cost
+      // more than they save (the unit is busy with ~1800 row requests per chunk); these go through the LSU.
+      // x / cs / dt: every CTA; the B / C tiles (shared by the heads of a group): the group's first head only.
+      if (TV_SSD_PF > 0) {
+        const bool group_leader = (h % hpg) == 0;
+        for (int cp = 0; cp < n; ++cp) {
+          if (cp >= TV_SSD_PF) while (*progress < cp - TV_SSD_PF + 1) __nanosleep(64);
+          const int t0 = cp * Q;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) zz[j] = 0u;
-#pragma unroll
-        for (int cb = 0; cb < 8; ++cb) tmem_st16(tmem + T_M0 + lane_base + cb * 16, zz);
-        tmem_st_wait();
-      }
-      const int kb_lo = helper ? 0 : (q == 3 ? 2 : q);          // first block of this warp
-      const int kb_hi = helper ? (q == 3 ? 2 : (q == 0 ? 0 : q)) : q + 1;   // one past its last block
-      for (int c = 0; c < n; ++c) {
-        const int s = c & 1, u = c >> 1;
-        float* sF = reinterpret_cast<float*>(smem + OFF_F + s * FBUF);
-        float Em = 0.f, um;
-        if (!helper) {
-          const float* sCS = reinterpret_cast<const float*>(smem + OFF_X + s * XSTAGE + TILE_X);
-          const float* sDT = sCS + 128;
-          mbar_wait(&bars[FULLX0 + s], u & 1);
-          const float cs_m = sCS[m], dt_m = sDT[m];
-          Em = cs_m * LOG2E;
-          sF[m] = __log2f(dt_m) - Em;            // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
-          // v_k for the row quarters that lie after this token's own quarter:  V_q'[k] = dt_k exp(cs[32q'-1] - cs_k)
-#pragma unroll
-          for (int qq = 1; qq < 4; ++qq)
-            if (qq > q) sF[qq * 128 + m] = dt_m * ex2_approx((sCS[32 * qq - 1] - cs_m) * LOG2E);
-          um = q > 0 ? ex2_approx((cs_m - sCS[32 * q - 1]) * LOG2E) : 0.f;     // u_m = exp(cs_m - ref) <= 1
-          sF[4 * 128 + m] = um;
-          named_bar_sync(1, 128);
-          if (lane == 0) { mbar_arrive(&bars[FRDY0 + s]); mbar_arrive(&bars[EMPTYX0 + s]); }
-        } else {
-          mbar_wait(&bars[FRDY0 + s], u & 1);
-          um = sF[4 * 128 + m];
+          for (int i = 0; i < 4; ++i) {
+            const int t = t0 + i * 32 + lane;
+            if (t < a.L) {
+              const char* px = reinterpret_cast<const char*>(a.xp + (int64_t)b * a.xbs + (int64_t)t * a.xss + (int64_t)h * a.xhs);
+              prefetch_l2(px); prefetch_l2(px + 128);
+              if (group_leader) {
+                const char* pb = reinterpret_cast<const char*>(a.bp + (int64_t)b * a.bbs + (int64_t)t * a.bss + (int64_t)g * a.bgs);
+                const char* pc = reinterpret_cast<const char*>(a.cp + (int64_t)b * a.cbs + (int64_t)t * a.css + (int64_t)g * a.cgs);
+                prefetch_l2(pb); prefetch_l2(pb + 128); prefetch_l2(pc); prefetch_l2(pc + 128);
+              }
+            }
+          }
+          if (lane < 8) {
+            const float* row = (lane < 4 ? a.cs : a.dt_act) + (row0 + (int64_t)cp * a.H) * Q;
+            prefetch_l2(reinterpret_cast<const char*>(row) + (lane & 3) * 128);
+          }
         }
-        mbar_wait(&bars[CBFULL], c & 1);
-        tc_fence_after();
-        if (threadIdx.x == 0) TV_TRACE(5, c);
-        const uint32_t tcb = tmem + T_CB + lane_base;
-        const uint32_t tm = tmem + (s ? T_M1 : T_M0) + lane_base;
+      }
+    } else if (warp == W_MMA) {
+      // =========================== MMA issuer: four streams (S, O, D, G), polled ===========================
+      // One thread issues every MMA, a whole group of 8 at a time (groups of different shapes issued concurrently from
+      // two threads interleave on the tensor pipe), but it never WAITS for a group in program order: each pass over
+      // the four streams issues whichever next group has all its inputs, state path (S, O) first.
+      if (elect_one()) {
+        constexpr uint32_t ID_CB = umma_idesc_bf16(128, 128, false, false);
+        constexpr uint32_t ID_Y = umma_idesc_bf16(128, P, false, true);
+        constexpr uint32_t ID_ST = umma_idesc_bf16(128, P, true, true);
+        const uint32_t sbase = smem_u32(smem);
+        // descriptor templates; per-MMA offsets are added to the 14-bit start-address field (units of 16 bytes)
+        const uint64_t dB_k = umma_smem_desc(sbase + OFF_B, 16, 1024, SWZ_128B);        // B as K-major operand (G)
+        const uint64_t dB_mn = umma_smem_desc(sbase + OFF_B, 16384, 1024, SWZ_128B);    // B as MN-major A operand (S)
+        const uint64_t dC_k = umma_smem_desc(sbase + OFF_C, 16, 1024, SWZ_128B);
+        const uint64_t dX = umma_smem_desc(sbase + OFF_X, 4096, 256, SWZ_32B);
+        const uint64_t dXS = umma_smem_desc(sbase + OFF_XS, 4096, 256, SWZ_32B);
+        const uint64_t dS = umma_smem_desc(sbase + OFF_S, 4096, 256, SWZ_32B);
+        // The issue loops are fully unrolled with compile-time descriptor offsets: a rolled loop costs ~110 cycles per
+        // MMA on the single issuing thread (descriptor arithmetic + R2UR), which made issue the bottleneck.
+        int cS = 0, cO = 0, cD = 0, cG = 0;          // next chunk of each stream
+        int dDone = 0;                               // D groups known to be complete (YDFULL phases observed)
+#ifdef TV_ENABLE_TRACE
+        long long passes = 0;
+#endif
 #pragma unroll 1
-        for (int kb = kb_lo; kb < (TV_ABLATE(1) ? kb_lo : kb_hi); ++kb) {   // rolled on purpose: one copy of each block body in the I-cache
-          if (kb < q) m_block_offdiag(tcb + kb * 32, tm + kb * 16, sF + q * 128 + kb * 32, um);
-          else m_block<DFOLD>(tcb + kb * 32, tm + kb * 16, sF + kb * 32, Em, lane, Dh, true);
+        while (cO < n || cD < n) {
+#ifdef TV_ENABLE_TRACE
+          ++passes;
+#endif
+          // ---- S(c): dS = B^T . xs  (fresh accumulator; WG_S has drained dS(c-1))
+          if (cS < n) {
+            const int c = cS, s = c & 1, u = c >> 1;
+            if (mbar_test_wait(&bars[XSFULL], c & 1) && mbar_test_wait(&bars[FULLB0 + s], u & 1) &&
+                (c == 0 || mbar_test_wait(&bars[DSFREE], (c - 1) & 1))) {
+              tc_fence_after();
+              TV_TRACE(2, c);
+#ifdef TV_ENABLE_TRACE
+              if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) a.trace[(int64_t)c * 16 + 10] = passes;
+#endif
+              const uint64_t db = umma_desc_advance(dB_mn, (uint32_t)(s * (TILE_BC >> 4)));
+              if (!TV_ABLATE(7))
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                umma_ss(tmem + T_DS, umma_desc_advance(db, j * 128), umma_desc_advance(dXS, j * 32), ID_ST, j > 0);
+              umma_commit(&bars[STDONE]);
+              umma_commit(&bars[EMPTYB0 + s]);
+              ++cS;
+            }
+          }
+          // ---- O(c): Yo = C . S_c   (only after S(c): see the note on YOFULL above the kernel)
+          if (cO < cS) {
+            const int c = cO, s = c & 1, u = c >> 1;
+            if (mbar_test_wait(&bars[SFULL], c & 1) && mbar_test_wait(&bars[FULLC0 + s], u & 1) &&
+                (c == 0 || mbar_test_wait(&bars[YOFREE], (c - 1) & 1))) {
+              tc_fence_after();
+              TV_TRACE(3, c);
+              const uint64_t dc = umma_desc_advance(dC_k, (uint32_t)(s * (TILE_BC >> 4)));
+              if (!TV_ABLATE(5))
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
+                umma_ss(tmem + T_YO, umma_desc_advance(dc, o), umma_desc_advance(dS, j * 32), ID_Y, j > 0);
+              }
+              umma_commit(&bars[YOFULL]);
+              umma_commit(&bars[EMPTYC0 + s]);
+              ++cO;
+            }
+          }
+          // ---- D(c): Yd = M . x   (A = M(c), packed bf16, columns 0..63 of its C.B^T buffer)
+          if (cD < cG) {
+            const int c = cD, s = c & 1, u = c >> 1;
+            if (mbar_test_wait(&bars[MFULL0 + s], u & 1) && mbar_test_wait(&bars[FULLX0 + s], u & 1) &&
+                (c == 0 || mbar_test_wait(&bars[YDFREE], (c - 1) & 1))) {
+              while (dDone < c) { mbar_wait(&bars[YDFULL], dDone & 1); ++dDone; }   // complete already (YDFREE(c-1))
+              tc_fence_after();
+              TV_TRACE(4, c);
+              const uint64_t dx = umma_desc_advance(dX, (uint32_t)(s * (XSTAGE >> 4)));
+              const uint32_t tmA = tmem + (s ? T_CB1 : T_CB0);
+              if (!TV_ABLATE(6))
+#pragma unroll
+              for (int j = 0; j < 8; ++j) umma_ts(tmem + T_YD, tmA + j * 8, umma_desc_advance(dx, j * 32), ID_Y, j > 0);
+              umma_commit(&bars[YDFULL]);
+              umma_commit(&bars[EMPTYX0 + s]);
+              ++cD;
+            }
+          }
+          // ---- G(c): C.B^T, up to two chunks ahead of D; overwrites the buffer that held M(c-2)
+          if (cG < n && cG <= cD + 1) {
+            const int c = cG, s = c & 1, u = c >> 1;
+            if (dDone < c - 1 && mbar_test_wait(&bars[YDFULL], dDone & 1)) ++dDone;
+            if (dDone >= c - 1 && mbar_test_wait(&bars[FULLB0 + s], u & 1) && mbar_test_wait(&bars[FULLC0 + s], u & 1)) {
+              tc_fence_after();
+              TV_TRACE(1, c);
+              const uint32_t so = (uint32_t)(s * (TILE_BC >> 4));
+              const uint64_t dc = umma_desc_advance(dC_k, so), db = umma_desc_advance(dB_k, so);
+              const uint32_t tcb = tmem + (s ? T_CB1 : T_CB0);
+              if (!TV_ABLATE(4))
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t o = (uint32_t)(((j >> 2) * 16384 + (j & 3) * 32) >> 4);
+                umma_ss(tcb, umma_desc_advance(dc, o), umma_desc_advance(db, o), ID_CB, j > 0);
+              }
+              umma_commit(&bars[CBFULL0 + s]);
+              umma_commit(&bars[EMPTYB0 + s]);
+              umma_commit(&bars[EMPTYC0 + s]);
+              ++cG;
+            }
+          }
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&bars[MFULL0 + s]); mbar_arrive(&bars[CBEMPTY]); }
-        if (threadIdx.x == 0) TV_TRACE(6, c);
       }
     }
-  } else if (warp < W_C) {
-    // =========================== WG_B: xs = w.x, state decay and bf16 state copy ===========================
-    const int r = threadIdx.x - W_B * 32, lane = threadIdx.x & 31;   // token row of x / state row n
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    float logsum = 0.f;
+  } else if (warp < W_X) {
+    // =========================== WG_A: M = C.B^T (.) decay, in place ===========================
+    // Row quarter q (TMEM lanes 32q..32q+31, reachable only from warps with id % 4 == q) owns q+1 blocks of 32 columns of
+    // C.B^T.  Packed M block kb goes to columns 16kb..16kb+15 of the same buffer, i.e. over C.B^T block kb/2 <= kb, which
+    // this warp has already read when it walks its blocks in ascending order.  The blocks above the diagonal are zeroed
+    // every chunk (the buffer is overwritten by the next C.B^T).  Nothing on the state path (x scaling, state fold)
+    // waits for this warpgroup.
+    reg_set<REG_A>();
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float Dh = (DFOLD && a.D != nullptr) ? a.D[h] : 0.f;
+    float* scr = reinterpret_cast<float*>(smem + OFF_SCR + warp * SCR);      // V[96] | F[32]
+    uint32_t zz[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) zz[j] = 0u;
+    for (int c = 0; c < n; ++c) {
+      const int s = c & 1, u = c >> 1;
+      const float* sCS = reinterpret_cast<const float*>(smem + OFF_X + s * XSTAGE + TILE_X);
+      const float* sDT = sCS + 128;
+      mbar_wait(&bars[FULLX0 + s], u & 1);
+      const float cs_m = sCS[m], dt_m = sDT[m];
+      const float Em = cs_m * LOG2E;
+      float um = 0.f;
+      __syncwarp();                              // every lane is done with the previous chunk's factors
+      scr[96 + lane] = __log2f(dt_m) - Em;       // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
+      if (q > 0) {                               // off-diagonal blocks: v_k = dt_k exp(ref - cs_k), ref = cs[32q-1]
+        const float ref = sCS[32 * q - 1];
+        um = ex2_approx((cs_m - ref) * LOG2E);   // u_m = exp(cs_m - ref) <= 1
+        for (int kb = 0; kb < q; ++kb)
+          scr[kb * 32 + lane] = sDT[kb * 32 + lane] * ex2_approx((ref - sCS[kb * 32 + lane]) * LOG2E);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);
+      mbar_wait(&bars[CBFULL0 + s], u & 1);
+      tc_fence_after();
+      if (threadIdx.x == 96) TV_TRACE(5, c);
+      const uint32_t tcb = tmem + (s ? T_CB1 : T_CB0) + lane_base;
+      if (!TV_ABLATE(1)) {
+        uint32_t pk[16];
+#pragma unroll 1
+        for (int kb = 0; kb < q; ++kb) {           // rolled on purpose: one copy of the block body in the I-cache
+          m_offdiag(tcb + kb * 32, pk, scr + kb * 32, um);
+          tmem_st16(tcb + kb * 16, pk);
+        }
+        m_diag<DFOLD>(tcb + q * 32, pk, scr + 96, Em, lane, Dh);
+        tmem_st16(tcb + q * 16, pk);
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+          if (j > q) tmem_st16(tcb + j * 16, zz);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[MFULL0 + s]);
+      if (threadIdx.x == 96) TV_TRACE(6, c);
+    }
+  } else if (warp < W_S) {
+    // =========================== WG_X: xs = w.x for the S MMA ===========================
+    reg_set<REG_X>();
+    const int r = threadIdx.x - W_X * 32;        // token row of x
     for (int c = 0; c < n; ++c) {
       const int s = c & 1, u = c >> 1;
       const uint8_t* xst = smem + OFF_X + s * XSTAGE;
@@ -423,204 +485,210 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       if (r == 0) TV_TRACE(7, c);
       const float cs_last = sCS[Q - 1];
       const float w_r = sDT[r] * __expf(cs_last - sCS[r]);
-      const float a_c = __expf(cs_last);
-      logsum += cs_last;
       const __nv_bfloat162 w2 = __float2bfloat162_rn(w_r);
-      // ---- xs = w_r * x into registers now (off the recurrence chain); stored once the xs buffer is free
+      // ---- xs = w_r * x into registers now; stored once S(c-1) has consumed the previous xs
       uint32_t xs[40];
+      if (!TV_ABLATE(13))
 #pragma unroll
-      for (int q = 0; q < 10; ++q) {
-        uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, q));
+      for (int qq = 0; qq < 10; ++qq) {
+        uint4 v = *reinterpret_cast<const uint4*>(xst + off_sw32(r, qq));
         __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
 #pragma unroll
         for (int i = 0; i < 4; ++i) hv[i] = __hmul2(hv[i], w2);
-        xs[4 * q] = v.x; xs[4 * q + 1] = v.y; xs[4 * q + 2] = v.z; xs[4 * q + 3] = v.w;
+        xs[4 * qq] = v.x; xs[4 * qq + 1] = v.y; xs[4 * qq + 2] = v.z; xs[4 * qq + 3] = v.w;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);
-      // ---- previous state MMA done: the xs buffer is free and S_c (entering state) is complete in TMEM
-      if (c > 0) { mbar_wait(&bars[STDONE], (c - 1) & 1); tc_fence_after(); }
+      if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);     // the raw x tile and cs / dt have been read
+      if (c > 0) mbar_wait(&bars[STDONE], (c - 1) & 1);
       if (r == 0) TV_TRACE(8, c);
+      if (!TV_ABLATE(13))
 #pragma unroll
-      for (int q = 0; q < 10; ++q)
-        *reinterpret_cast<uint4*>(smem + OFF_XS + off_sw32(r, q)) = make_uint4(xs[4 * q], xs[4 * q + 1], xs[4 * q + 2], xs[4 * q + 3]);
-      // ---- state row n = r: decay in place (critical path) and bf16 copy of the un-decayed entering state.
-      //      O(c-1) is issued right behind S(c-1), so the copy buffer is (almost always) already free here.
-      if (FULL && c > 0) mbar_wait(&bars[YOFFDONE], (c - 1) & 1);
-      if (!TV_ABLATE(2))
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {       // 48 + 32 columns: two TMEM round trips instead of five
-        const int c0 = half * 48, nc = half ? 2 : 3;
-        uint32_t v[48];
-        if (c == 0) {
-#pragma unroll
-          for (int j = 0; j < 48; ++j)
-            if (j < nc * 16)
-              v[j] = a.init == nullptr ? 0u : __float_as_uint(a.init[(((int64_t)b * a.H + h) * P + c0 + j) * N + r]);
-        } else {
-#pragma unroll
-          for (int pc = 0; pc < 3; ++pc)
-            if (pc < nc) tmem_ld16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
-          tmem_ld_wait();
-        }
-        if (FULL) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q)
-            if (q < 2 * nc) {
-              const int j = 8 * q;
-              *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, (c0 >> 3) + q)) =
-                  make_uint4(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
-                             pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
-                             pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
-                             pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 48; j += 2)
-          if (j < nc * 16) {
-            const float2 d2 = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(a_c, a_c));
-            v[j] = __float_as_uint(d2.x); v[j + 1] = __float_as_uint(d2.y);
-          }
-#pragma unroll
-        for (int pc = 0; pc < 3; ++pc)
-          if (pc < nc) tmem_st16(tmem + T_ST + lane_base + c0 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
-      }
-      tmem_st_wait();
-      tc_fence_before();
+      for (int qq = 0; qq < 10; ++qq)
+        *reinterpret_cast<uint4*>(smem + OFF_XS + off_sw32(r, qq)) = make_uint4(xs[4 * qq], xs[4 * qq + 1], xs[4 * qq + 2], xs[4 * qq + 3]);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&bars[XSFULL]); mbar_arrive(&bars[SDECAY]); if (FULL) mbar_arrive(&bars[SFULL]); }
-      if (r == 0) TV_TRACE(9, c);
+      if (lane == 0) mbar_arrive(&bars[XSFULL]);
+      if (r == 96) TV_TRACE(9, c);
     }
-    // ---- final state = state after the last chunk
-    mbar_wait(&bars[STDONE], (n - 1) & 1);
-    tc_fence_after();
+  } else if (warp < W_C) {
+    // =========================== WG_S: the running state, in registers ===========================
+    // Thread r holds row n = r of the 128x80 fp32 state.  Per chunk: S_{c+1} = exp(cs_last) S_c + dS(c), then the bf16
+    // copy of S_{c+1} that O(c+1) reads goes to shared memory once O(c) has finished with the previous copy.
+    reg_set<REG_S>();
+    const int r = threadIdx.x - W_S * 32;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float st[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) st[j] = a.init == nullptr ? 0.f : a.init[(((int64_t)b * a.H + h) * P + j) * N + r];
+    auto write_copy = [&]() {
+#pragma unroll
+      for (int qq = 0; qq < 10; ++qq)
+        *reinterpret_cast<uint4*>(smem + OFF_S + off_sw32(r, qq)) =
+            make_uint4(pack_bf16x2(st[8 * qq], st[8 * qq + 1]), pack_bf16x2(st[8 * qq + 2], st[8 * qq + 3]),
+                       pack_bf16x2(st[8 * qq + 4], st[8 * qq + 5]), pack_bf16x2(st[8 * qq + 6], st[8 * qq + 7]));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[SFULL]);
+    };
+    write_copy();
+    float logsum = 0.f;
+    float cs_next = a.cs[row0 * Q + (Q - 1)];
+    for (int c = 0; c < n; ++c) {
+      const float cs_last = cs_next;
+      if (c + 1 < n) cs_next = a.cs[(row0 + (int64_t)(c + 1) * a.H) * Q + (Q - 1)];
+      const float a_c = __expf(cs_last);
+      logsum += cs_last;
+      mbar_wait(&bars[STDONE], c & 1);
+      tc_fence_after();
+      if (!TV_ABLATE(2)) {
+        uint32_t v[48];
+#pragma unroll
+        for (int pc = 0; pc < 3; ++pc) tmem_ld16(tmem + T_DS + lane_base + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 48; ++j) st[j] = fmaf(a_c, st[j], __uint_as_float(v[j]));
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) tmem_ld16(tmem + T_DS + lane_base + 48 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[pc * 16]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[DSFREE]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[48 + j] = fmaf(a_c, st[48 + j], __uint_as_float(v[j]));
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[DSFREE]);
+      }
+      if (c + 1 < n) {
+        mbar_wait(&bars[YOFULL], c & 1);           // O(c) has read the copy of S_c
+        write_copy();
+      }
+      if (r == 0) TV_TRACE(14, c);
+    }
     if (a.fin != nullptr) {
 #pragma unroll
-      for (int pc = 0; pc < 5; ++pc) {
-        uint32_t v[16];
-        tmem_ld16(tmem + T_ST + lane_base + pc * 16, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          a.fin[(((int64_t)b * a.H + h) * P + pc * 16 + j) * N + r] = __uint_as_float(v[j]);
-      }
+      for (int j = 0; j < P; ++j) a.fin[(((int64_t)b * a.H + h) * P + j) * N + r] = st[j];
     }
     if (a.logdecay != nullptr && r == 0) a.logdecay[(int64_t)b * a.H + h] = logsum;
-  } else if (warp < W_PROD) {
+  } else {
     // =========================== WG_C: epilogue  y = Yd + exp(cs_m) Yo + D x  [* silu(z)] ===========================
-    if (FULL) {
-      const int r = threadIdx.x - W_C * 32, lane = threadIdx.x & 31;   // token row m
-      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-      const float* sD = reinterpret_cast<const float*>(smem + OFF_D);
-      for (int c = 0; c < n; ++c) {
-        const int s = c & 1, u = c >> 1;
-        uint8_t* xst = smem + OFF_X + s * XSTAGE;
-        const int t = c * Q + r;
-        // y(c-1) was staged in the other x stage and handed to TMA: once TMA has read it, that stage goes back to the
-        // producer (this replaces the D(c-1) commit; waiting here costs nothing, YFULL(c) is still far away)
-        if (c > 0) {
-          if (threadIdx.x == W_C * 32) { tma_store_wait_read(); mbar_arrive(&bars[EMPTYX0 + (s ^ 1)]); }
-          __syncwarp();
-        }
-        float e_r;
-        if (!DFOLD) {
-          mbar_wait(&bars[FULLX0 + s], u & 1);
-          e_r = __expf(reinterpret_cast<const float*>(xst + TILE_X)[r]);
-        } else {
-          e_r = __expf(a.cs[(row0 + (int64_t)c * a.H) * Q + r]);   // one coalesced 512-byte row per chunk (L2 hit)
-        }
-        const __nv_bfloat16* zrow = HAS_Z ? a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs : nullptr;
-        mbar_wait(&bars[YFULL], c & 1);
-        tc_fence_after();
-        if (r == 0) TV_TRACE(11, c);
-        // Software-pipelined drain: the TMEM loads of round pc+1 are in flight while round pc is combined and stored;
-        // the accumulators are handed back as soon as the last load has landed, before the last round's math.
-        uint32_t ydA[16], yoA[16], ydB[16], yoB[16];
-        tmem_ld16(tmem + T_YD + lane_base, ydA);
-        tmem_ld16(tmem + T_YO + lane_base, yoA);
-        tmem_ld_wait();
-        auto finish_round = [&](int pc, const uint32_t (&yd)[16], const uint32_t (&yo)[16]) {
-          float xv[16];
-          if (!DFOLD) {                              // explicit D*x path ((H,P)-shaped D): x row from the x stage
-            const uint4 xa = *reinterpret_cast<const uint4*>(xst + off_sw32(r, 2 * pc));
-            const uint4 xb = *reinterpret_cast<const uint4*>(xst + off_sw32(r, 2 * pc + 1));
-            const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              xv[2 * j] = sD[pc * 16 + 2 * j] * __uint_as_float(xw[j] << 16);
-              xv[2 * j + 1] = sD[pc * 16 + 2 * j + 1] * __uint_as_float(xw[j] & 0xffff0000u);
-            }
-          }
-          float zv[16];
-          if (HAS_Z) {
-            uint4 za = make_uint4(0, 0, 0, 0), zb = za;
-            if (t < a.L) { za = *reinterpret_cast<const uint4*>(zrow + pc * 16); zb = *reinterpret_cast<const uint4*>(zrow + pc * 16 + 8); }
-            const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              zv[2 * j] = silu<true>(__uint_as_float(zw[j] << 16));
-              zv[2 * j + 1] = silu<true>(__uint_as_float(zw[j] & 0xffff0000u));
-            }
-          }
-          uint32_t pk[8];
+    // Each warp owns 32 token rows end to end: drain, combine, stage its bf16 piece in its own 3 KB staging area and write
+    // it with its own TMA stores, in two passes (columns 0..47, then 48..79 over the first two atoms once TMA has read them).
+    reg_set<REG_C>();
+    const int r = threadIdx.x - W_C * 32;          // token row m
+    const int wq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const float* sD = reinterpret_cast<const float*>(smem + OFF_D);
+    uint8_t* ystg = smem + OFF_Y + wq * YSTG;
+    for (int c = 0; c < n; ++c) {
+      const int s = c & 1, u = c >> 1;
+      const uint8_t* xst = smem + OFF_X + s * XSTAGE;
+      const int t = c * Q + r;
+      const float e_r = __expf(a.cs[(row0 + (int64_t)c * a.H) * Q + r]);   // one coalesced 512-byte row per chunk (L2 hit)
+      const __nv_bfloat16* zrow = HAS_Z ? a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs : nullptr;
+      const bool rows_live = c * Q + wq * 32 < a.L;
+      if (!DFOLD) mbar_wait(&bars[FULLX0 + s], u & 1);
+      mbar_wait(&bars[YDFULL], c & 1);
+      mbar_wait(&bars[YOFULL], c & 1);
+      tc_fence_after();
+      if (r == 0) TV_TRACE(11, c);
+      // Software-pipelined drain: the TMEM loads of round pc+1 are in flight while round pc is combined and stored;
+      // the accumulators are handed back as soon as the last load has landed, before the last round's math.
+      uint32_t ydA[16], yoA[16], ydB[16], yoB[16];
+      tmem_ld16(tmem + T_YD + lane_base, ydA);
+      tmem_ld16(tmem + T_YO + lane_base, yoA);
+      if (lane == 0) tma_store_wait_read();        // the staging atoms of the previous chunk's second pass have been read
+      __syncwarp();
+      tmem_ld_wait();
+      auto finish_round = [&](int pc, const uint32_t (&yd)[16], const uint32_t (&yo)[16]) {
+        float xv[16];
+        if (!DFOLD) {                              // explicit D*x path ((H,P)-shaped D): x row from the x stage
+          const uint4 xa = *reinterpret_cast<const uint4*>(xst + off_sw32(r, 2 * pc));
+          const uint4 xb = *reinterpret_cast<const uint4*>(xst + off_sw32(r, 2 * pc + 1));
+          const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float2 y2 = __ffma2_rn(make_float2(e_r, e_r), make_float2(__uint_as_float(yo[2 * j]), __uint_as_float(yo[2 * j + 1])),
-                                         make_float2(__uint_as_float(yd[2 * j]), __uint_as_float(yd[2 * j + 1])));
-            float y0 = y2.x, y1 = y2.y;
-            if (!DFOLD) { y0 += xv[2 * j]; y1 += xv[2 * j + 1]; }
-            if (HAS_Z) { y0 *= zv[2 * j]; y1 *= zv[2 * j + 1]; }
-            pk[j] = pack_bf16x2(y0, y1);
-          }
-          // stage the bf16 row piece in the (dead) x tile of this chunk, same SW32 atom layout: 160 conflict-free
-          // wavefronts per chunk instead of 640 scattered 32-byte global stores; TMA writes it out and clips the tail
-          if (!TV_ABLATE(11)) {
-            *reinterpret_cast<uint4*>(xst + off_sw32(r, 2 * pc)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(xst + off_sw32(r, 2 * pc + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-        };
-        if (TV_ABLATE(0)) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[YEMPTY]);
-        } else
-#pragma unroll
-        for (int pc = 0; pc < 5; pc += 2) {
-          if (pc + 1 < 5) {
-            tmem_ld16(tmem + T_YD + lane_base + (pc + 1) * 16, ydB);
-            tmem_ld16(tmem + T_YO + lane_base + (pc + 1) * 16, yoB);
-          }
-          finish_round(pc, ydA, yoA);
-          if (pc + 1 < 5) {
-            tmem_ld_wait();
-            if (pc + 2 < 5) {
-              tmem_ld16(tmem + T_YD + lane_base + (pc + 2) * 16, ydA);
-              tmem_ld16(tmem + T_YO + lane_base + (pc + 2) * 16, yoA);
-            }
-            finish_round(pc + 1, ydB, yoB);
-            if (pc + 2 < 5) tmem_ld_wait();
-          }
-          if (pc + 2 == 4) {                           // the last loads (round 4) have landed: release Yd / Yo now
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[YEMPTY]);
+            xv[2 * j] = sD[pc * 16 + 2 * j] * __uint_as_float(xw[j] << 16);
+            xv[2 * j + 1] = sD[pc * 16 + 2 * j + 1] * __uint_as_float(xw[j] & 0xffff0000u);
           }
         }
-        fence_proxy_async();                         // the staged tile becomes visible to the async proxy (TMA)
-        named_bar_sync(2, 128);
-        if (threadIdx.x == W_C * 32) {
-          if (!TV_ABLATE(11)) {
+        float zv[16];
+        if (HAS_Z) {
+          uint4 za = make_uint4(0, 0, 0, 0), zb = za;
+          if (t < a.L) { za = *reinterpret_cast<const uint4*>(zrow + pc * 16); zb = *reinterpret_cast<const uint4*>(zrow + pc * 16 + 8); }
+          const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
 #pragma unroll
-            for (int i = 0; i < 5; ++i) tma_store_4d(&maps.y, xst + i * 4096, 16 * i, h, c * Q, b);
+          for (int j = 0; j < 8; ++j) {
+            zv[2 * j] = silu<true>(__uint_as_float(zw[j] << 16));
+            zv[2 * j + 1] = silu<true>(__uint_as_float(zw[j] & 0xffff0000u));
+          }
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 y2 = __ffma2_rn(make_float2(e_r, e_r), make_float2(__uint_as_float(yo[2 * j]), __uint_as_float(yo[2 * j + 1])),
+                                       make_float2(__uint_as_float(yd[2 * j]), __uint_as_float(yd[2 * j + 1])));
+          float y0 = y2.x, y1 = y2.y;
+          if (!DFOLD) { y0 += xv[2 * j]; y1 += xv[2 * j + 1]; }
+          if (HAS_Z) { y0 *= zv[2 * j]; y1 *= zv[2 * j + 1]; }
+          pk[j] = pack_bf16x2(y0, y1);
+        }
+        // stage the 32-byte row piece: atom pc (first pass) or pc-3 (second pass), SW32 layout; TMA clips the ragged tail
+        if (!TV_ABLATE(11)) {
+          uint8_t* at = ystg + (pc < 3 ? pc : pc - 3) * 1024 + lane * 32;
+          const uint32_t sw = (uint32_t)((lane >> 2) & 1) << 4;
+          *reinterpret_cast<uint4*>(at + sw) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(at + (sw ^ 16u)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      };
+      auto store_pass = [&](int first, int count) {   // atoms first..first+count-1 of y -> global
+        fence_proxy_async();                       // the staged piece becomes visible to the async proxy (TMA)
+        __syncwarp();
+        if (lane == 0) {
+          if (!TV_ABLATE(11) && rows_live) {
+            for (int i = 0; i < (TV_ABLATE(15) ? 1 : count); ++i)
+              tma_store_4d(&maps.y, ystg + i * 1024, 16 * (first + i), h, c * Q + wq * 32, b);
           }
           tma_store_commit();
         }
+      };
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&bars[YDFREE]); mbar_arrive(&bars[YOFREE]); }
         if (r == 0) TV_TRACE(12, c);
-        if (r == 0) TV_TRACE(13, c);
+      };
+      if (TV_ABLATE(0)) {
+        release_acc();
+      } else {
+        // rounds: 0 (A) 1 (B) 2 (A) | 3 (B) 4 (A)
+        tmem_ld16(tmem + T_YD + lane_base + 16, ydB);
+        tmem_ld16(tmem + T_YO + lane_base + 16, yoB);
+        finish_round(0, ydA, yoA);
+        tmem_ld_wait();
+        tmem_ld16(tmem + T_YD + lane_base + 32, ydA);
+        tmem_ld16(tmem + T_YO + lane_base + 32, yoA);
+        finish_round(1, ydB, yoB);
+        tmem_ld_wait();
+        tmem_ld16(tmem + T_YD + lane_base + 48, ydB);
+        tmem_ld16(tmem + T_YO + lane_base + 48, yoB);
+        finish_round(2, ydA, yoA);
+        tmem_ld16(tmem + T_YD + lane_base + 64, ydA);
+        tmem_ld16(tmem + T_YO + lane_base + 64, yoA);
+        store_pass(0, 3);
+        tmem_ld_wait();
+        release_acc();                             // the last loads have landed: hand Yd / Yo back
+        if (lane == 0) tma_store_wait_read();      // first pass read: atoms 0 and 1 are free again
+        __syncwarp();
+        finish_round(3, ydB, yoB);
+        finish_round(4, ydA, yoA);
+        store_pass(3, 2);
       }
-      if (threadIdx.x == W_C * 32) tma_store_wait_all();
+      if (!DFOLD) { __syncwarp(); if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]); }   // x rows read
+      if (r == 0) TV_TRACE(13, c);
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -942,7 +1010,7 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
       }
       const uint64_t dy[4] = {(uint64_t)P, (uint64_t)p.nheads, L, (uint64_t)p.batch};
       const uint64_t sy[3] = {(uint64_t)P * 2, (uint64_t)p.nheads * P * 2, (uint64_t)L * p.nheads * P * 2};
-      const uint32_t by[4] = {16, 1, (uint32_t)Q, 1};
+      const uint32_t by[4] = {16, 1, 32, 1};          // one epilogue warp's rows per store
       if (!encode_bf16_tmap(&maps.y, p.out, 4, dy, sy, by, CU_TENSOR_MAP_SWIZZLE_32B)) {
         set_error("ssd(tcgen05): cuTensorMapEncodeTiled(out) failed");
         return TV_ERR_CUDA;
@@ -959,6 +1027,10 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
   a.trace = (long long*)g_trace_ptr;
   a.ablate = g_ablate;
   a.zbs = p.z_batch_stride; a.zss = p.z_seq_stride; a.zhs = p.z_head_stride;
+  a.xp = (const __nv_bfloat16*)p.x; a.bp = (const __nv_bfloat16*)p.B; a.cp = (const __nv_bfloat16*)p.C;
+  a.xbs = p.x_batch_stride; a.xss = p.x_seq_stride; a.xhs = p.x_head_stride;
+  a.bbs = p.b_batch_stride; a.bss = p.b_seq_stride; a.bgs = p.b_group_stride;
+  a.cbs = p.c_batch_stride; a.css = p.c_seq_stride; a.cgs = p.c_group_stride;
   dim3 grid(p.nheads, p.batch);
   auto launch = [&](auto kern) -> int {
     TV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -985,8 +1057,8 @@ int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
     }
     lrc = TV_OK;
   }
-  else if (p.z != nullptr) lrc = dfold ? launch(ssd_fused_kernel<true, true, true>) : launch(ssd_fused_kernel<true, true, false>);
-  else lrc = dfold ? launch(ssd_fused_kernel<true, false, true>) : launch(ssd_fused_kernel<true, false, false>);
+  else if (p.z != nullptr) lrc = dfold ? launch(ssd_fused_kernel<true, true>) : launch(ssd_fused_kernel<true, false>);
+  else lrc = dfold ? launch(ssd_fused_kernel<false, true>) : launch(ssd_fused_kernel<false, false>);
   if (lrc != TV_OK) return lrc;
   TV_LAUNCH_OK();
   return TV_OK;

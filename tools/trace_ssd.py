@@ -20,8 +20,8 @@ _lib.load().tv_debug_set_trace(None)
 tall = buf.cpu().view(2 * n, 16)
 t = tall[:n]
 ta = tall[n:]
-names = ["P:Bempty_ok", "I:G full_ok", "I:S issue", "I:O issue", "I:D issue", "A:cbfull", "A:m_done", "B:full_ok",
-         "B:stdone_ok", "B:sdecay", "B:sfull", "C:yfull(c)", "C:yempty(c)", "C:epi_done(c)", "P:Xempty_ok"]
+names = ["P:x issue", "I:G issue", "I:S issue", "I:O issue", "I:D issue", "A:cbfull", "A:m_done", "X:x landed",
+         "X:stdone(c-1)", "X3:xs written", "I:passes", "C:yfull(c)", "C:acc freed", "C:epi_done(c)", "S:fold+copy"]
 t0 = int(t[t > 0].min())
 c0, c1 = n // 2, n // 2 + 4
 print("chunk | " + " | ".join(f"{nm:>14}" for nm in names))
