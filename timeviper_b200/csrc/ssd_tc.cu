@@ -50,11 +50,11 @@ constexpr int Q = 128, P = 80, N = 128;
 #define TV_SSD_PF 0
 #endif
 constexpr int THREADS = 640;
-constexpr int W_A = 0, W_X = 4, W_S = 8, W_C = 12, W_PROD = 16, W_MMA = 17, W_PF = 18;   // first warp of each role
+constexpr int W_A = 0, W_X = 4, W_S = 8, W_C = 12, W_PROD = 16, W_MMA = 17;   // warps 18 / 19: M helpers   // first warp of each role
 // Registers per thread after setmaxnreg.  The pool is what the CTA was LAUNCHED with (640 threads x 96 registers, the
 // most __launch_bounds__(640) allows), not the SM's register file: the five warpgroups must sum to 5 x 96 = 480.
 constexpr int REG_LAUNCH = 96;
-constexpr int REG_A = 104, REG_X = 72, REG_S = 136, REG_C = 104, REG_MISC = 64;
+constexpr int REG_A = 104, REG_X = 64, REG_S = 136, REG_C = 96, REG_MISC = 80;
 static_assert(REG_A + REG_X + REG_S + REG_C + REG_MISC <= 5 * REG_LAUNCH, "register pool of the CTA");
 template <int R> __device__ __forceinline__ void reg_set() {      // executed by all four warps of a warpgroup
   if (R > REG_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
@@ -67,8 +67,8 @@ constexpr uint32_t OFF_B = 0, OFF_C = 2 * TILE_BC, OFF_X = 4 * TILE_BC;         
 constexpr uint32_t OFF_XS = OFF_X + 2 * XSTAGE, OFF_S = OFF_XS + TILE_X, OFF_Y = OFF_S + TILE_X;
 constexpr uint32_t YSTG = 3 * 1024;              // per epilogue warp: three 32-row x 16-column SW32 atoms of staged y
 constexpr uint32_t OFF_SCR = OFF_Y + 4 * YSTG;
-constexpr uint32_t SCR = 512;                    // per-warp fp32 scratch of the 4 M-building warps (decay factors)
-constexpr uint32_t OFF_D = OFF_SCR + 4 * SCR;    // 80 floats (D row), padded to 512
+constexpr uint32_t SCR = 512;                    // per-warp fp32 scratch of the 6 M-building warps (decay factors)
+constexpr uint32_t OFF_D = OFF_SCR + 6 * SCR;    // 80 floats (D row), padded to 512
 constexpr uint32_t OFF_BAR = OFF_D + 512;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 512 + 1024;   // + barriers + alignment slack
 static_assert(OFF_XS % 1024 == 0 && OFF_S % 1024 == 0 && XSTAGE % 256 == 0, "tile alignment");
@@ -77,7 +77,7 @@ static_assert(SMEM_BYTES <= kMaxDynSmem, "smem budget");
 constexpr uint32_t T_CB0 = 0, T_CB1 = 128, T_YD = 256, T_YO = 336, T_DS = 416;
 
 enum Bar { FULLB0 = 0, FULLB1, EMPTYB0, EMPTYB1, FULLC0, FULLC1, EMPTYC0, EMPTYC1, FULLX0, FULLX1, EMPTYX0, EMPTYX1,
-           CBFULL0, CBFULL1, MFULL0, MFULL1, XSFULL, STDONE, DSFREE, SFULL, YOFULL, YDFULL, YDFREE, YOFREE,
+           CBFULL0, CBFULL1, MFULL0, MFULL1, HREAD0, HREAD1, XSFULL, STDONE, DSFREE, SFULL, YOFULL, YDFULL, YDFREE, YOFREE,
            NBAR };
 static_assert(NBAR * 8 + 8 <= 512, "barrier area");
 
@@ -146,6 +146,36 @@ __device__ __forceinline__ void m_diag(uint32_t t_src, uint32_t (&pk)[16], const
   }
 }
 
+// Diagonal block without transcendentals: exp(cs_m - cs_k) dt_k = u_m * v_k around ref = cs just before the block's rows,
+// u_m = exp(cs_m - ref) <= 1, v_k = dt_k exp(ref - cs_k) >= dt_k.  v_k grows with the decay inside the block, so the caller
+// takes this path only while the block's total decay keeps exp(ref - cs_k) far from overflow (masked entries k > m are
+// finite and dropped by a select, never multiplied by zero); otherwise m_diag with its 32 exponentials per row.
+template <bool DFOLD>
+__device__ __forceinline__ void m_diag_fast(uint32_t t_src, uint32_t (&pk)[16], const float* __restrict__ sVk, float um,
+                                            int lane, float Dh) {
+  uint32_t r[32];
+  tmem_ld32(t_src, r);
+  const float2 um2 = make_float2(um, um);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float4 v4 = *reinterpret_cast<const float4*>(sVk + 2 * j);
+    const float2 e0 = __fmul2_rn(make_float2(v4.x, v4.y), um2), e1 = __fmul2_rn(make_float2(v4.z, v4.w), um2);
+    float2 a0 = __fmul2_rn(e0, make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+    float2 a1 = __fmul2_rn(e1, make_float2(__uint_as_float(r[2 * j + 2]), __uint_as_float(r[2 * j + 3])));
+    if (2 * j > lane) a0.x = 0.f;                  // causal mask
+    if (2 * j + 1 > lane) a0.y = 0.f;
+    if (2 * j + 2 > lane) a1.x = 0.f;
+    if (2 * j + 3 > lane) a1.y = 0.f;
+    if (DFOLD && 2 * j == lane) a0.x += Dh;        // D skip folded into the diagonal
+    if (DFOLD && 2 * j + 1 == lane) a0.y += Dh;
+    if (DFOLD && 2 * j + 2 == lane) a1.x += Dh;
+    if (DFOLD && 2 * j + 3 == lane) a1.y += Dh;
+    pk[j] = pack_bf16x2(a0.x, a0.y);
+    pk[j + 1] = pack_bf16x2(a1.x, a1.y);
+  }
+}
+
 // Off-diagonal 32x32 block (every k of the block precedes every row of this warp): the decay factorises without
 // overflow around ref = cs at the last token before the warp's rows,
 //   exp(cs_m - cs_k) dt_k = u_m * v_k,   u_m = exp(cs_m - ref) <= 1,   v_k = dt_k exp(ref - cs_k) <= dt_k,
@@ -197,9 +227,11 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[FULLB0 + i], 1); mbar_init(&bars[FULLC0 + i], 1); mbar_init(&bars[FULLX0 + i], 1);
       mbar_init(&bars[EMPTYB0 + i], 2); mbar_init(&bars[EMPTYC0 + i], 2);   // one commit from each issuer
-      mbar_init(&bars[EMPTYX0 + i], DFOLD ? 9 : 13);   // one lane per WG_A and WG_X warp + the D commit (+ WG_C: explicit D*x)
+      // one lane per WG_X warp + the D commit (+ WG_C for the explicit D*x path)
+      mbar_init(&bars[EMPTYX0 + i], DFOLD ? 5 : 9);
       mbar_init(&bars[CBFULL0 + i], 1);
-      mbar_init(&bars[MFULL0 + i], 4);
+      mbar_init(&bars[MFULL0 + i], 6);               // 4 WG_A warps + 2 helper warps
+      mbar_init(&bars[HREAD0 + i], 2);
     }
     mbar_init(&bars[XSFULL], 4); mbar_init(&bars[STDONE], 1); mbar_init(&bars[DSFREE], 4); mbar_init(&bars[SFULL], 4);
     mbar_init(&bars[YOFULL], 1); mbar_init(&bars[YDFULL], 1); mbar_init(&bars[YDFREE], 4); mbar_init(&bars[YOFREE], 4);
@@ -271,36 +303,6 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
               }
               ++cc;
             }
-          }
-        }
-      }
-    } else if (warp == W_PF) {
-      // =========================== L2 prefetch warp ===========================
-      // Plain prefetch.global.L2 of the lines of chunk c + TV_SSD_PF, paced by the producer's progress counter, so that the
-      // TMA loads (whose latency sits in every ring of this kernel) hit L2.  Prefetches issued THROUGH the TMA unit cost
-      // more than they save (the unit is busy with ~1800 row requests per chunk); these go through the LSU.
-      // x / cs / dt: every CTA; the B / C tiles (shared by the heads of a group): the group's first head only.
-      if (TV_SSD_PF > 0) {
-        const bool group_leader = (h % hpg) == 0;
-        for (int cp = 0; cp < n; ++cp) {
-          if (cp >= TV_SSD_PF) while (*progress < cp - TV_SSD_PF + 1) __nanosleep(64);
-          const int t0 = cp * Q;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int t = t0 + i * 32 + lane;
-            if (t < a.L) {
-              const char* px = reinterpret_cast<const char*>(a.xp + (int64_t)b * a.xbs + (int64_t)t * a.xss + (int64_t)h * a.xhs);
-              prefetch_l2(px); prefetch_l2(px + 128);
-              if (group_leader) {
-                const char* pb = reinterpret_cast<const char*>(a.bp + (int64_t)b * a.bbs + (int64_t)t * a.bss + (int64_t)g * a.bgs);
-                const char* pc = reinterpret_cast<const char*>(a.cp + (int64_t)b * a.cbs + (int64_t)t * a.css + (int64_t)g * a.cgs);
-                prefetch_l2(pb); prefetch_l2(pb + 128); prefetch_l2(pc); prefetch_l2(pc + 128);
-              }
-            }
-          }
-          if (lane < 8) {
-            const float* row = (lane < 4 ? a.cs : a.dt_act) + (row0 + (int64_t)cp * a.H) * Q;
-            prefetch_l2(reinterpret_cast<const char*>(row) + (lane & 3) * 128);
           }
         }
       }
@@ -414,54 +416,109 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
           }
         }
       }
+    } else {
+      // =========================== helper warps 18 / 19: off-diagonal blocks 0 and 1 of row quarters 2 / 3 ===========================
+      // WG_A's warp of the same quarter writes its packed blocks over C.B^T block 1 and may do so once HREAD says that
+      // this warp's load of block 1 has landed.
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      float* scr = reinterpret_cast<float*>(smem + OFF_SCR + (4 + q - 2) * SCR);      // V[64]
+      // cs / dt of the next chunk are fetched from global memory (L2) one chunk ahead, NOT from the x stage: M(c) must be
+      // ready when x(c) lands, so that D(c) can run at once and hand the x stage back to the TMA producer.
+      const float* gcs = a.cs + row0 * Q;
+      const float* gdt = a.dt_act + row0 * Q;
+      const int64_t cstride = (int64_t)a.H * Q;
+      float n_csm = gcs[m], n_ref = gcs[32 * q - 1], n_cs0 = gcs[lane], n_cs1 = gcs[32 + lane], n_dt0 = gdt[lane], n_dt1 = gdt[32 + lane];
+      for (int c = 0; c < n; ++c) {
+        const int s = c & 1, u = c >> 1;
+        const float ref = n_ref;
+        const float um = ex2_approx((n_csm - ref) * LOG2E);                // u_m = exp(cs_m - ref) <= 1
+        __syncwarp();
+        scr[lane] = n_dt0 * ex2_approx((ref - n_cs0) * LOG2E);             // v_k = dt_k exp(ref - cs_k) <= dt_k
+        scr[32 + lane] = n_dt1 * ex2_approx((ref - n_cs1) * LOG2E);
+        __syncwarp();
+        if (c + 1 < n) {
+          const float* ncs = gcs + (c + 1) * cstride;
+          const float* ndt = gdt + (c + 1) * cstride;
+          n_csm = ncs[m]; n_ref = ncs[32 * q - 1]; n_cs0 = ncs[lane]; n_cs1 = ncs[32 + lane]; n_dt0 = ndt[lane]; n_dt1 = ndt[32 + lane];
+        }
+        mbar_wait(&bars[CBFULL0 + s], u & 1);
+        tc_fence_after();
+        const uint32_t tcb = tmem + (s ? T_CB1 : T_CB0) + lane_base;
+        uint32_t pk[16];
+        if (!TV_ABLATE(1)) {
+          m_offdiag(tcb, pk, scr, um);
+          tmem_st16(tcb, pk);                        // over C.B^T block 0, which only this warp reads
+          m_offdiag(tcb + 32, pk, scr + 32, um);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[HREAD0 + s]);
+        if (!TV_ABLATE(1)) {
+          tmem_st16(tcb + 16, pk);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[MFULL0 + s]);
+      }
     }
   } else if (warp < W_X) {
     // =========================== WG_A: M = C.B^T (.) decay, in place ===========================
     // Row quarter q (TMEM lanes 32q..32q+31, reachable only from warps with id % 4 == q) owns q+1 blocks of 32 columns of
-    // C.B^T.  Packed M block kb goes to columns 16kb..16kb+15 of the same buffer, i.e. over C.B^T block kb/2 <= kb, which
-    // this warp has already read when it walks its blocks in ascending order.  The blocks above the diagonal are zeroed
-    // every chunk (the buffer is overwritten by the next C.B^T).  Nothing on the state path (x scaling, state fold)
-    // waits for this warpgroup.
+    // C.B^T; packed M block kb goes to columns 16kb..16kb+15 of the same buffer, i.e. over C.B^T block kb/2.  Ten blocks
+    // over six warps, at most two each: this warp takes the diagonal block plus block 0 (q = 1) or block 2 (q = 3); the
+    // helper warps 18 / 19 take blocks 0 and 1 of quarters 2 / 3, and this warp stores over C.B^T block 1 only after
+    // HREAD (their loads have landed).  The blocks above the diagonal are zeroed every chunk (the buffer is overwritten
+    // by the next C.B^T).  Nothing on the state path (x scaling, state fold) waits for these warps.
     reg_set<REG_A>();
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float Dh = (DFOLD && a.D != nullptr) ? a.D[h] : 0.f;
-    float* scr = reinterpret_cast<float*>(smem + OFF_SCR + warp * SCR);      // V[96] | F[32]
+    float* scr = reinterpret_cast<float*>(smem + OFF_SCR + warp * SCR);      // V[32] (off-diagonal block) | F[32] (diagonal)
+    const int kbo = q > 0 ? q - 1 : 0;           // the off-diagonal block of quarters 1 and 3 (its last cs is `ref`)
     uint32_t zz[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) zz[j] = 0u;
+    // cs / dt of the next chunk are fetched from global memory (L2) one chunk ahead, NOT from the x stage: M(c) must be
+    // ready when x(c) lands, so that D(c) can run at once and hand the x stage back to the TMA producer.
+    const float* gcs = a.cs + row0 * Q;
+    const float* gdt = a.dt_act + row0 * Q;
+    const int64_t cstride = (int64_t)a.H * Q;
+    float n_csm = gcs[m], n_dtm = gdt[m], n_cso = gcs[kbo * 32 + lane], n_dto = gdt[kbo * 32 + lane];
     for (int c = 0; c < n; ++c) {
       const int s = c & 1, u = c >> 1;
-      const float* sCS = reinterpret_cast<const float*>(smem + OFF_X + s * XSTAGE + TILE_X);
-      const float* sDT = sCS + 128;
-      mbar_wait(&bars[FULLX0 + s], u & 1);
-      const float cs_m = sCS[m], dt_m = sDT[m];
-      const float Em = cs_m * LOG2E;
-      float um = 0.f;
-      __syncwarp();                              // every lane is done with the previous chunk's factors
-      scr[96 + lane] = __log2f(dt_m) - Em;       // F_k = log2(dt_k) - cs_k*log2e  (dt = 0 -> -inf -> weight 0)
-      if (q > 0) {                               // off-diagonal blocks: v_k = dt_k exp(ref - cs_k), ref = cs[32q-1]
-        const float ref = sCS[32 * q - 1];
-        um = ex2_approx((cs_m - ref) * LOG2E);   // u_m = exp(cs_m - ref) <= 1
-        for (int kb = 0; kb < q; ++kb)
-          scr[kb * 32 + lane] = sDT[kb * 32 + lane] * ex2_approx((ref - sCS[kb * 32 + lane]) * LOG2E);
+      const float cs_m = n_csm, dt_m = n_dtm, cs_o = n_cso, dt_o = n_dto;
+      if (c + 1 < n) {
+        const float* ncs = gcs + (c + 1) * cstride;
+        const float* ndt = gdt + (c + 1) * cstride;
+        n_csm = ncs[m]; n_dtm = ndt[m]; n_cso = ncs[kbo * 32 + lane]; n_dto = ndt[kbo * 32 + lane];
       }
+      const float Em = cs_m * LOG2E;
+      const float ref = q > 0 ? __shfl_sync(0xffffffffu, cs_o, 31) : 0.f;   // cs just before this warp's rows
+      const bool fast = ref - __shfl_sync(0xffffffffu, cs_m, 31) < 60.f;    // decay inside the diagonal block (warp-uniform)
+      const float um = ex2_approx((cs_m - ref) * LOG2E);                    // u_m = exp(cs_m - ref) <= 1
+      __syncwarp();                              // every lane is done with the previous chunk's factors
+      // diagonal block: v_k = dt_k exp(ref - cs_k) (fast path) or F_k = log2(dt_k) - cs_k*log2e (dt = 0 -> -inf -> weight 0)
+      scr[32 + lane] = fast ? dt_m * ex2_approx((ref - cs_m) * LOG2E) : __log2f(dt_m) - Em;
+      if (q & 1) scr[lane] = dt_o * ex2_approx((ref - cs_o) * LOG2E);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[EMPTYX0 + s]);
       mbar_wait(&bars[CBFULL0 + s], u & 1);
       tc_fence_after();
       if (threadIdx.x == 96) TV_TRACE(5, c);
       const uint32_t tcb = tmem + (s ? T_CB1 : T_CB0) + lane_base;
+      uint32_t pko[16], pkd[16];
       if (!TV_ABLATE(1)) {
-        uint32_t pk[16];
-#pragma unroll 1
-        for (int kb = 0; kb < q; ++kb) {           // rolled on purpose: one copy of the block body in the I-cache
-          m_offdiag(tcb + kb * 32, pk, scr + kb * 32, um);
-          tmem_st16(tcb + kb * 16, pk);
-        }
-        m_diag<DFOLD>(tcb + q * 32, pk, scr + 96, Em, lane, Dh);
-        tmem_st16(tcb + q * 16, pk);
+        if (q & 1) m_offdiag(tcb + kbo * 32, pko, scr, um);
+        if (fast) m_diag_fast<DFOLD>(tcb + q * 32, pkd, scr + 32, um, lane, Dh);
+        else m_diag<DFOLD>(tcb + q * 32, pkd, scr + 32, Em, lane, Dh);
+      }
+      if (q >= 2) { mbar_wait(&bars[HREAD0 + s], u & 1); tc_fence_after(); }
+      if (!TV_ABLATE(1)) {
+        if (q & 1) tmem_st16(tcb + kbo * 16, pko);
+        tmem_st16(tcb + q * 16, pkd);
 #pragma unroll
         for (int j = 1; j < 4; ++j)
           if (j > q) tmem_st16(tcb + j * 16, zz);
