@@ -643,7 +643,14 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
       const uint8_t* xst = smem + OFF_X + s * XSTAGE;
       const int t = c * Q + r;
       const float e_r = __expf(a.cs[(row0 + (int64_t)c * a.H) * Q + r]);   // one coalesced 512-byte row per chunk (L2 hit)
-      const __nv_bfloat16* zrow = HAS_Z ? a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs : nullptr;
+      // z gate: the row's 160 bytes are fetched now, ahead of the waits, so that no round of the drain sees a global load
+      uint4 zr[HAS_Z ? 10 : 1];
+      if (HAS_Z) {
+        const __nv_bfloat16* zrow = a.z + b * a.zbs + (int64_t)t * a.zss + (int64_t)h * a.zhs;
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+          zr[HAS_Z ? i : 0] = t < a.L ? *reinterpret_cast<const uint4*>(zrow + i * 8) : make_uint4(0, 0, 0, 0);
+      }
       const bool rows_live = c * Q + wq * 32 < a.L;
       if (!DFOLD) mbar_wait(&bars[FULLX0 + s], u & 1);
       mbar_wait(&bars[YDFULL], c & 1);
@@ -672,8 +679,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         }
         float zv[16];
         if (HAS_Z) {
-          uint4 za = make_uint4(0, 0, 0, 0), zb = za;
-          if (t < a.L) { za = *reinterpret_cast<const uint4*>(zrow + pc * 16); zb = *reinterpret_cast<const uint4*>(zrow + pc * 16 + 8); }
+          const uint4 za = zr[HAS_Z ? 2 * pc : 0], zb = zr[HAS_Z ? 2 * pc + 1 : 0];
           const uint32_t zw[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

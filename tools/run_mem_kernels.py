@@ -31,3 +31,4 @@ def timeit(fn, nbytes, name):
 
 timeit(lambda: tv.causal_conv1d_fn(xBC.transpose(1, 2), w, b, activation="silu"), 49152, "conv1d+silu")
 timeit(lambda: tv.rmsnorm_fn(y, nw, None, z=gate, eps=1e-5, group_size=1280, norm_before_gate=False), 61440, "gated rmsnorm")
+timeit(lambda: tv.rmsnorm_fn(y, nw, None, z=None, eps=1e-5, group_size=1280, norm_before_gate=False), 40960, "rmsnorm without z (gate fused upstream)")
