@@ -482,6 +482,80 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_hybrid(args):
+    """BASELINE.json configs[3]: prefill of the 56-layer Nanov2-9B-shaped hybrid LM (random init) over 5K frames of synthetic
+    video tokens (81,920 tokens), Mamba-2 layers on this package's kernels, attention on library SDPA, MLP and projections
+    on cuBLAS, last-token lm_head.  One GPU.  A step = one whole prefill from token embeddings resident in HBM to the fp32
+    logits of the last position."""
+    import timeviper_b200 as tv
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus != 1:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"metric": "hybrid_prefill_tokens_per_s", "unavailable": "the hybrid stack is single-GPU (the sequence-sharded layer loop is not built)"}))
+        return
+    torch.cuda.set_device(0)
+    L = args.seqlen if args.seqlen != 131072 else 81920
+    cfg = tv.Mamba2Config.nanov2_9b_hybrid()
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = tv.HybridCausalLM(cfg).to(torch.bfloat16).eval()
+    x = torch.randn(1, L, cfg.hidden_size, device="cuda").to(torch.bfloat16)
+    share = {}
+    ev = []
+
+    def pre(m, a):
+        e = torch.cuda.Event(enable_timing=True); e.record(); m._e0 = e
+
+    def post(m, a, o):
+        e = torch.cuda.Event(enable_timing=True); e.record(); ev.append((m.block_type, m._e0, e))
+    for _ in range(max(args.warmup, 1)):
+        logits = model(inputs_embeds=x)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = tv.launch_count()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        logits = model(inputs_embeds=x)
+    e1.record(); torch.cuda.synchronize()
+    clocks = sampler.stop(t0, time.time())
+    launches = tv.launch_count() - n0
+    ms = e0.elapsed_time(e1) / args.steps
+    hooks = []
+    for layer in model.backbone.layers:
+        hooks += [layer.register_forward_pre_hook(pre), layer.register_forward_hook(post)]
+    logits = model(inputs_embeds=x); torch.cuda.synchronize()
+    for kind, a, b in ev:
+        share[kind] = share.get(kind, 0.0) + a.elapsed_time(b)
+    for hk in hooks:
+        hk.remove()
+    # end to end through the public API with host buffers: pinned embeddings -> H2D -> prefill -> D2H of the logits
+    hx = torch.empty(x.shape, dtype=x.dtype).pin_memory(); hx.copy_(x.cpu())
+    hl = torch.empty(logits.shape, dtype=logits.dtype).pin_memory()
+    k = max(1, min(args.e2e_steps, 3))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(k):
+        hl.copy_(model(inputs_embeds=hx.cuda(non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / k * 1e3
+    pat = cfg.hybrid_override_pattern
+    print(json.dumps({
+        "metric": "hybrid_prefill_tokens_per_s", "value": L / ms * 1e3, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Nanov2-9B-shaped hybrid LM prefill (BASELINE.json configs[3]): 56 layers "
+                               f"({pat.count('M')} Mamba-2 / {pat.count('*')} attention / {pat.count('-')} MLP), random init, batch 1, "
+                               "last-token lm_head", "seqlen": L, "parallelism": "single",
+                   "params_B": round(sum(p.numel() for p in model.parameters()) / 1e9, 2),
+                   "l2": "activations (0.7 GB per layer boundary, 3.7 GB in_proj output) >> L2 (126 MB); no flush needed"},
+        "e2e": {"value": L / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "steps": k, "h2d_bytes_per_step": hx.numel() * 2,
+                "d2h_bytes_per_step": hl.numel() * 4, "api": "HybridCausalLM.forward(inputs_embeds) from pinned host embeddings to host logits"},
+        "gpu_launches": launches, "clocks": clocks,
+        "layer_time_share_ms": {k2: round(v, 1) for k2, v in sorted(share.items())},
+        "finite": bool(torch.isfinite(logits).all()),
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -496,8 +570,12 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (default: all host cores)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="back-to-back seconds for the sustained step time")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the three kernels eagerly instead of one CUDA graph")
+    ap.add_argument("--workload", default="mixer", choices=["mixer", "hybrid9b"],
+                    help="mixer: the BASELINE metric (default); hybrid9b: BASELINE.json configs[3], its own JSON line")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "hybrid9b" and args.impl == "ours":
+        run_hybrid(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -125,6 +125,44 @@ def main_hybrid():
         print(name, "last_hidden_state", tuple(hs.shape), "->", os.path.getsize(path) // 1024, "KiB")
 
 
+
+def main_causal_lm():
+    """NemotronHForCausalLM.forward (modeling_nano.py:2286-2292, :2414-2433): the hybrid backbone from token ids, then
+    ``lm_head(hidden_states).float()`` over the whole sequence.  Stored: the parameters (reference names, ``backbone.*`` +
+    ``lm_head.weight``), the token ids, the last hidden state and the fp32 logits of every position."""
+    import contextlib
+    mn, Cfg = load_reference()
+    torch.cuda.default_stream = lambda device=None: None
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    out_dir = os.path.join(HERE, "..", "tests", "golden")
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pattern, L, vocab = 96, 4, 80, 1, 128, 128, 4, 2, 24, 160, "M*M-", 200, 257
+    torch.manual_seed(97531)
+    cfg = Cfg(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, mamba_n_groups=G, ssm_state_size=N,
+              mamba_chunk_size=Q, mamba_d_conv=4, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+              layer_norm_epsilon=1e-5, num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd,
+              intermediate_size=mlp, vocab_size=vocab)
+    cfg._attn_implementation = "eager"
+    model = mn.NemotronHForCausalLM(cfg).float().eval()
+    with torch.no_grad():
+        for layer in model.backbone.layers:
+            if layer.block_type == "mamba":
+                layer.mixer.A_log.copy_(torch.log(torch.rand(H) * 15 + 1))
+                layer.mixer.dt_bias.copy_(torch.randn(H) * 0.5 - 2.0)
+                layer.mixer.D.copy_(torch.randn(H))
+            layer.norm.weight.copy_(1.0 + 0.1 * torch.randn(hidden))
+        model.lm_head.weight.copy_(torch.randn(vocab, hidden) * 0.2)
+        model.backbone.embeddings.weight.copy_(torch.randn(vocab, hidden))
+        ids = torch.randint(0, vocab, (1, L))
+        out = model(input_ids=ids, use_cache=False, return_dict=True)
+        hs = model.backbone(input_ids=ids, use_cache=False)
+        hs = hs[0] if isinstance(hs, tuple) else hs.last_hidden_state
+    blob = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    blob.update(input_ids=ids.numpy(), logits=out.logits.numpy(), last_hidden_state=hs.numpy(),
+                dims=np.array([hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, L, vocab], dtype=np.int64), pattern=np.array(pattern))
+    path = os.path.join(out_dir, "causal_lm_MsMd_ids200.npz")
+    np.savez_compressed(path, **blob)
+    print("causal_lm logits", tuple(out.logits.shape), out.logits.dtype, "->", os.path.getsize(path) // 1024, "KiB")
+
 def main_masked():
     """Batch 2, left-padded, with attention_mask: the reference multiplies the padded rows by zero before in_proj (:676)
     and again after the conv (:707; fast path :471 and :625-627), so that silu(conv bias) of a padded position never
@@ -161,7 +199,10 @@ def main_masked():
 if __name__ == "__main__":
     if "--masked-only" in sys.argv:
         main_masked()
+    elif "--causal-lm-only" in sys.argv:
+        main_causal_lm()
     else:
         main()
         main_hybrid()
         main_masked()
+        main_causal_lm()

@@ -385,3 +385,13 @@ def nemotron_random_params(hidden, H, P, G, N, K=4, seed=1234, n_layers=56, nond
         p["D"] = torch.randn(H, generator=g)
         p["norm.weight"] = 1.0 + 0.1 * torch.randn(d_inner, generator=g)
     return p
+
+
+def causal_lm_logits_ref(p: dict, input_ids: torch.Tensor, **hybrid_kw):
+    """NemotronHForCausalLM.forward (modeling_nano.py:2414-2433): embeddings -> hybrid backbone -> lm_head, fp32 logits of
+    every position.  p: the model's state_dict (``backbone.*`` + ``lm_head.weight``)."""
+    bb = {k[len("backbone."):]: v for k, v in p.items() if k.startswith("backbone.")}
+    dtype = hybrid_kw.get("dtype", torch.float32)
+    emb = F.embedding(input_ids, bb["embeddings.weight"].to(dtype))
+    h = hybrid_forward_ref(bb, emb, **hybrid_kw)
+    return F.linear(h, p["lm_head.weight"].to(dtype)).float()

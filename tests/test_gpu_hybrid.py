@@ -45,3 +45,29 @@ def test_hybrid_prefill_against_reference_golden(path, dtype, tol):
     ref = R.hybrid_forward_ref(sd, torch.from_numpy(z["inputs_embeds"]), pattern=pattern, num_heads=H, head_dim=P,
                                n_groups=G, ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd)
     assert relerr(out, ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_causal_lm_last_token_logits_against_reference_golden(dtype, tol):
+    """HybridCausalLM (reference parameter names, token ids in) against NemotronHForCausalLM.forward of the reference:
+    the last-token fp32 logits it returns by default, and the full tensor on request."""
+    import timeviper_b200 as tv
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "causal_lm_MsMd_ids200.npz"))
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, L, vocab = [int(v) for v in z["dims"]]
+    pattern = str(z["pattern"])
+    cfg = tv.Mamba2Config(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, n_groups=G, ssm_state_size=N,
+                          chunk_size=Q, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                          num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd, intermediate_size_mlp=mlp,
+                          vocab_size=vocab)
+    model = tv.HybridCausalLM(cfg)
+    skip = ("pattern", "dims", "input_ids", "logits", "last_hidden_state")
+    model.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files if k not in skip}, strict=True)
+    model = model.to(dtype).cuda().eval()
+    ids = torch.from_numpy(z["input_ids"]).cuda()
+    ref = torch.from_numpy(z["logits"])
+    last = model(input_ids=ids)
+    assert last.shape == (1, 1, vocab) and last.dtype == torch.float32
+    assert relerr(last, ref[:, -1:]) < tol
+    full = model(input_ids=ids, all_positions=True)
+    assert full.shape == (1, L, vocab) and relerr(full, ref) < tol
+    assert torch.equal(full[:, -1:], last)

@@ -167,3 +167,17 @@ def test_oracle_padding_mask_matches_reference_batch2(golden_dir):
     out_nomask, _, _ = R.mixer_forward_ref(sd, hs * mask[:, :, None], num_heads=H, head_dim=P, n_groups=G,
                                            ssm_state_size=N, chunk_size=Q, group_map="torch_forward")
     assert float((out_nomask[0] - ref[0]).abs().max() / ref.abs().max()) > 1e-3
+
+
+def test_causal_lm_logits_oracle_matches_reference_golden():
+    """NemotronHForCausalLM.forward of the reference (token ids -> fp32 logits of every position) against the oracle."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "causal_lm_MsMd_ids200.npz"))
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, L, vocab = [int(v) for v in z["dims"]]
+    skip = ("pattern", "dims", "input_ids", "logits", "last_hidden_state")
+    sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in skip}
+    logits = R.causal_lm_logits_ref(sd, torch.from_numpy(z["input_ids"]), pattern=str(z["pattern"]), num_heads=H, head_dim=P,
+                                    n_groups=G, ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd)
+    ref = torch.from_numpy(z["logits"])
+    assert logits.shape == ref.shape == (1, L, vocab) and logits.dtype == torch.float32
+    assert float((logits - ref).abs().max() / ref.abs().max()) < 2e-5

@@ -14,10 +14,10 @@ from .ops import (causal_conv1d_fn, causal_conv1d_update, fold_boundary_states, 
                   selective_state_update, ssd_kernel_family, launch_count)
 from .sharded import (sharded_mixer_forward, sharded_prefill_from_host, sharded_scan_core,  # noqa: E402
                       sharded_scan_core_graph)
-from .hybrid import HybridPrefillStack  # noqa: E402
+from .hybrid import HybridCausalLM, HybridPrefillStack  # noqa: E402
 
 __all__ = ["Mamba2Config", "Mamba2MixerPrefill", "MambaRMSNormGated", "patch_reference", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_chunk_scan_combined", "mamba_split_conv1d_scan_combined",
            "rmsnorm_fn", "selective_state_update", "mamba_chunk_state_summary", "fold_boundary_states",
            "ssd_kernel_family", "sharded_mixer_forward", "sharded_scan_core", "sharded_prefill_from_host", "sharded_scan_core_graph",
-           "HybridPrefillStack", "launch_count"]
+           "HybridPrefillStack", "HybridCausalLM", "launch_count"]

@@ -54,6 +54,19 @@ class Mamba2Config:
         return cls()
 
     @classmethod
+    def nanov2_9b_hybrid(cls, **kw):
+        """The 56-layer Nanov2-9B-shaped hybrid stack of BASELINE.json configs[3] (SURVEY.md section 8 header): attention at
+        layers 14 / 21 / 30 / 39, Mamba-2 and MLP layers alternating around them: 27 M / 4 * / 25 -."""
+        attn, pat, k = {14, 21, 30, 39}, [], 0
+        for i in range(56):
+            if i in attn:
+                pat.append("*")
+            else:
+                pat.append("M-"[k % 2]); k += 1
+        pat[len(pat) - 1 - pat[::-1].index("-")] = "M"
+        return cls(num_hidden_layers=56, hybrid_override_pattern="".join(pat), **kw)
+
+    @classmethod
     def small(cls, n_groups=1):
         """BASELINE.json configs[0]: the reference's CPU-runnable small config."""
         return cls(hidden_size=512, mamba_num_heads=16, mamba_head_dim=80, n_groups=n_groups,

@@ -49,6 +49,14 @@ constexpr int Q = 128, P = 80, N = 128;
 #ifndef TV_SSD_PF
 #define TV_SSD_PF 0
 #endif
+// Back-off of the two polling threads after a pass that found nothing to do (ns; 0 = spin).  Every probe is a shared-memory
+// operation, and the shared-memory pipe is what bounds this kernel.
+#ifndef TV_POLL_NS_PROD
+#define TV_POLL_NS_PROD 0
+#endif
+#ifndef TV_POLL_NS_MMA
+#define TV_POLL_NS_MMA 0
+#endif
 constexpr int THREADS = 640;
 constexpr int W_A = 0, W_X = 4, W_S = 8, W_C = 12, W_PROD = 16, W_MMA = 17;   // warps 18 / 19: M helpers   // first warp of each role
 // Registers per thread after setmaxnreg.  The pool is what the CTA was LAUNCHED with (640 threads x 96 registers, the
@@ -257,6 +265,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
         prefetch_tmap(&maps.x); prefetch_tmap(&maps.b); prefetch_tmap(&maps.c); prefetch_tmap(&maps.y);
         int cb = 0, cc = 0, cx = 0;
         while (cb < n || cc < n || cx < n) {
+          const int before = cb + cc + cx;
           if (cx < n) {
             const int s = cx & 1, u = cx >> 1;
             if (cx < 2 || mbar_test_wait(&bars[EMPTYX0 + s], (u - 1) & 1)) {
@@ -304,6 +313,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
               ++cc;
             }
           }
+          if (TV_POLL_NS_PROD > 0 && cb + cc + cx == before) __nanosleep(TV_POLL_NS_PROD);
         }
       }
     } else if (warp == W_MMA) {
@@ -332,6 +342,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
 #endif
 #pragma unroll 1
         while (cO < n || cD < n) {
+          const int before = cS + cO + cD + cG;
 #ifdef TV_ENABLE_TRACE
           ++passes;
 #endif
@@ -414,6 +425,7 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
               ++cG;
             }
           }
+          if (TV_POLL_NS_MMA > 0 && cS + cO + cD + cG == before) __nanosleep(TV_POLL_NS_MMA);
         }
       }
     } else {

@@ -98,11 +98,37 @@ class HybridPrefillStack(nn.Module):
     @torch.no_grad()
     def forward(self, input_ids=None, inputs_embeds=None, cache_params=None):
         """Prefill: (b, L) token ids or (b, L, hidden) embeddings -> last hidden states (b, L, hidden) after ``norm_f``.
-        ``cache_params`` (reference cache interface) receives the conv / SSM states of every Mamba-2 layer."""
+        ``cache_params`` (reference cache interface) receives the conv / SSM states of every Mamba-2 layer.
+        Limits (stated, not hidden): no ``attention_mask`` (batch 1 or unpadded batches only) and the attention layers do
+        not write a KV cache, so this stack prefills and scores the last position; token-by-token decode after it needs
+        the reference's attention cache and is not wired here."""
         if (input_ids is None) == (inputs_embeds is None):
             raise ValueError("exactly one of input_ids / inputs_embeds")
         h = self.embeddings(input_ids) if inputs_embeds is None else inputs_embeds
-        pos = torch.arange(h.shape[1], device=h.device)
+        pos = torch.arange(h.shape[1])          # on the HOST: the mixer branches on cache_position[0] > 0 (no device sync)
         for layer in self.layers:
             h = layer(h, cache_params=cache_params, cache_position=pos)
         return self.norm_f(h)
+
+
+class HybridCausalLM(nn.Module):
+    """``NemotronHForCausalLM`` for prefill (modeling_nano.py:2286-2292, forward :2414-2433): ``backbone`` + ``lm_head`` with
+    the reference's parameter names, so its ``state_dict`` loads strictly.
+
+    The reference projects EVERY position to the vocabulary and upcasts to fp32 (:2433) -- at 128K video tokens and the
+    131,072-entry Nanov2 vocabulary that is a 64 GiB tensor of which generation reads one row.  ``forward`` therefore returns
+    the fp32 logits of the LAST position by default (``(b, 1, vocab)``, bit-identical to the reference's ``logits[:, -1:]``
+    for the same hidden state); ``all_positions=True`` gives the reference's full ``(b, L, vocab)`` tensor."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.backbone = HybridPrefillStack(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, all_positions=False):
+        h = self.backbone(input_ids=input_ids, inputs_embeds=inputs_embeds, cache_params=cache_params)
+        if not all_positions:
+            h = h[:, -1:]
+        return self.lm_head(h.to(self.lm_head.weight.dtype)).float()
