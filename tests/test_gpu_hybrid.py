@@ -70,4 +70,4 @@ def test_causal_lm_last_token_logits_against_reference_golden(dtype, tol):
     assert relerr(last, ref[:, -1:]) < tol
     full = model(input_ids=ids, all_positions=True)
     assert full.shape == (1, L, vocab) and relerr(full, ref) < tol
-    assert torch.equal(full[:, -1:], last)
+    assert relerr(full[:, -1:], last) < (1e-5 if dtype == torch.float32 else 1e-2)   # same row; cuBLAS picks another kernel for M = 1

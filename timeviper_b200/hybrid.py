@@ -117,8 +117,8 @@ class HybridCausalLM(nn.Module):
 
     The reference projects EVERY position to the vocabulary and upcasts to fp32 (:2433) -- at 128K video tokens and the
     131,072-entry Nanov2 vocabulary that is a 64 GiB tensor of which generation reads one row.  ``forward`` therefore returns
-    the fp32 logits of the LAST position by default (``(b, 1, vocab)``, bit-identical to the reference's ``logits[:, -1:]``
-    for the same hidden state); ``all_positions=True`` gives the reference's full ``(b, L, vocab)`` tensor."""
+    the fp32 logits of the LAST position by default (``(b, 1, vocab)``: the reference's ``logits[:, -1:]`` up to the
+    summation order of the GEMM); ``all_positions=True`` gives the reference's full ``(b, L, vocab)`` tensor."""
 
     def __init__(self, config):
         super().__init__()
