@@ -163,6 +163,54 @@ def main_causal_lm():
     np.savez_compressed(path, **blob)
     print("causal_lm logits", tuple(out.logits.shape), out.logits.dtype, "->", os.path.getsize(path) // 1024, "KiB")
 
+
+def main_pdrop():
+    """TransV / pyramid-drop between layers: NemotronHModel.forward with ``use_pdrop`` (the hooks at
+    modeling_nano.py:1634-1689 -> flash_rank_drop :2156 -> pdrop_no_pack :1779-2095), inference, batch 1, ``no_merge`` (the
+    default of evaluate.py:167-177): a uniform drop before one layer and attention-ranked drops (query = last prompt token,
+    keys = the vision tokens, softmax averaged over heads, top-k) before two attention layers."""
+    import contextlib
+    mn, Cfg = load_reference()
+    torch.cuda.default_stream = lambda device=None: None
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    out_dir = os.path.join(HERE, "..", "tests", "golden")
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pattern = 96, 4, 80, 1, 128, 128, 4, 2, 24, 160, "M-M*M-*M"
+    pre, V, post = 5, 120, 20
+    pdrop_type = "uni_1_0.8-attn_3_0.5-attn_6_0.25"
+    torch.manual_seed(8642)
+    cfg = Cfg(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, mamba_n_groups=G, ssm_state_size=N,
+              mamba_chunk_size=Q, mamba_d_conv=4, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+              layer_norm_epsilon=1e-5, num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd,
+              intermediate_size=mlp, vocab_size=100, use_pdrop=True, pdrop_type=pdrop_type, merge_module="no_merge")
+    cfg._attn_implementation = "eager"
+    model = mn.NemotronHModel(cfg).float().eval()
+    for k, v in model.pdrop_args.items():          # what NemotronHForCausalLM.set_pdrop_args does (:2459-2462)
+        setattr(model, k, v)
+    # The reference rebuilds the causal mask after a drop from the OLD cache_position (:1663-1665), which only works when
+    # _update_causal_mask returns None, i.e. with flash_attention_2 (:2208-2213) -- the configuration TimeViper runs.
+    # flash-attn needs a GPU, so the harness builds the math attention class ("eager", which takes mask None as causal,
+    # :1099-1107) and then tells _update_causal_mask that the implementation is flash_attention_2.
+    model.config._attn_implementation = "flash_attention_2"
+    with torch.no_grad():
+        for layer in model.layers:
+            if layer.block_type == "mamba":
+                layer.mixer.A_log.copy_(torch.log(torch.rand(H) * 15 + 1))
+                layer.mixer.dt_bias.copy_(torch.randn(H) * 0.5 - 2.0)
+                layer.mixer.D.copy_(torch.randn(H))
+            layer.norm.weight.copy_(1.0 + 0.1 * torch.randn(hidden))
+        x = torch.randn(1, pre + V + post, hidden)
+        args = dict(is_interleaved=False, first_vision_token_positions=[torch.tensor(pre)], num_vision_tokens=[V],
+                    text_prompt_lens=[pre + post])
+        out = model(inputs_embeds=x, use_cache=False, return_dict=True, train_pdrop_args=args)
+    hs = out.last_hidden_state
+    blob = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    blob.update(inputs_embeds=x.numpy(), last_hidden_state=hs.numpy(),
+                dims=np.array([hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pre, V, post], dtype=np.int64),
+                pattern=np.array(pattern), pdrop_type=np.array(pdrop_type))
+    path = os.path.join(out_dir, "pdrop_uni_attn_attn.npz")
+    np.savez_compressed(path, **blob)
+    print("pdrop", tuple(x.shape), "->", tuple(hs.shape), os.path.getsize(path) // 1024, "KiB")
+
 def main_masked():
     """Batch 2, left-padded, with attention_mask: the reference multiplies the padded rows by zero before in_proj (:676)
     and again after the conv (:707; fast path :471 and :625-627), so that silu(conv bias) of a padded position never
@@ -201,6 +249,8 @@ if __name__ == "__main__":
         main_masked()
     elif "--causal-lm-only" in sys.argv:
         main_causal_lm()
+    elif "--pdrop-only" in sys.argv:
+        main_pdrop()
     else:
         main()
         main_hybrid()

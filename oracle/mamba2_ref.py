@@ -313,15 +313,60 @@ def rmsnorm_ref(x, weight, eps, dtype=torch.float32):
     return weight.to(dtype) * (h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + eps))
 
 
+def parse_pdrop_type(pdrop_type: str):
+    """'type_layer_ratio-...' -> (types, layers, ratios with a leading 1)   (modeling_nano.py:1469-1477)"""
+    parts = [t.split("_") for t in pdrop_type.split("-")]
+    return [t[0] for t in parts], [int(t[1]) for t in parts], [1.0] + [float(t[2]) for t in parts]
+
+
+def pdrop_select_ref(h, stage, kind, ratios, wq, wk, attn_heads, kv_heads, attn_head_dim, vision_index, num_vision_tokens,
+                     text_prompt_len):
+    """pdrop_no_pack for inference, one sample (modeling_nano.py:1779-1988): the sorted sequence indices of the vision
+    tokens that survive stage `stage`, and the index of the first token after the vision block.  h: (L, hidden)."""
+    image_tokens = int(num_vision_tokens * ratios[stage])                                       # :1795-1802
+    keep = int(num_vision_tokens * ratios[stage + 1])
+    if "attn" in kind:
+        L = h.shape[0]
+        q = F.linear(h, wq).view(L, attn_heads, attn_head_dim).transpose(0, 1)                   # :1833-1845 (raw features)
+        k = F.linear(h, wk).view(L, kv_heads, attn_head_dim).transpose(0, 1)
+        k = k.repeat_interleave(attn_heads // kv_heads, dim=0)
+        pq = text_prompt_len + image_tokens - 1                                                  # :1917-1924: last prompt token
+        w = (q[:, pq:pq + 1] @ k.transpose(1, 2)) / math.sqrt(attn_head_dim)                     # (heads, 1, L)
+        mask = torch.zeros(L, dtype=h.dtype)
+        mask[pq + 1:] = float("-inf")                                                            # the causal row of the query
+        w = F.softmax(w + mask, dim=-1, dtype=torch.float32).to(h.dtype)                         # :1932-1937
+        w = w.mean(0)[:, vision_index:vision_index + image_tokens].mean(0)                       # :1939-1943
+        top = w.topk(keep).indices
+    elif "uni" in kind:
+        top = torch.linspace(0, image_tokens - 1, keep, dtype=torch.long)                        # :1950-1957
+    else:
+        raise NotImplementedError(kind)
+    return (top + vision_index).sort().values, vision_index + image_tokens                      # :1961-1965
+
+
 def hybrid_forward_ref(p: dict, inputs_embeds: torch.Tensor, *, pattern: str, num_heads: int, head_dim: int,
                        n_groups: int, ssm_state_size: int, chunk_size: int, attn_heads: int, kv_heads: int,
-                       attn_head_dim: int, eps: float = 1e-5, group_map: str = "kernel", dtype=torch.float32):
+                       attn_head_dim: int, eps: float = 1e-5, group_map: str = "kernel", dtype=torch.float32,
+                       pdrop: dict = None):
     """p: a NemotronHModel state_dict (layers.N.norm.weight, layers.N.mixer.*, norm_f.weight).  Returns the last hidden
-    states (b, L, hidden) after norm_f."""
+    states (b, L, hidden) after norm_f.  pdrop = dict(pdrop_type, first_vision_token_position, num_vision_tokens,
+    text_prompt_len): TransV / pyramid-drop before the listed layers (batch 1, no merge module)."""
     h = inputs_embeds.to(dtype)
     b, L, _ = h.shape
+    if pdrop is not None:
+        assert b == 1
+        kinds, layers, ratios = parse_pdrop_type(pdrop["pdrop_type"])
     for i, kind in enumerate(pattern):
         pre = f"layers.{i}."
+        if pdrop is not None and i in layers:                                                      # :1634-1666
+            st = layers.index(i)
+            wq = p.get(pre + "mixer.q_proj.weight"); wk = p.get(pre + "mixer.k_proj.weight")
+            top, start = pdrop_select_ref(h[0], st, kinds[st], ratios, None if wq is None else wq.to(dtype),
+                                          None if wk is None else wk.to(dtype), attn_heads, kv_heads, attn_head_dim,
+                                          pdrop["first_vision_token_position"], pdrop["num_vision_tokens"], pdrop["text_prompt_len"])
+            vi = pdrop["first_vision_token_position"]
+            h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)                            # :1981-1988
+            L = h.shape[1]
         x = rmsnorm_ref(h, p[pre + "norm.weight"], eps, dtype)                                    # :941
         sub = {k[len(pre) + 6:]: v for k, v in p.items() if k.startswith(pre + "mixer.")}
         if kind == "M":

@@ -71,3 +71,33 @@ def test_causal_lm_last_token_logits_against_reference_golden(dtype, tol):
     full = model(input_ids=ids, all_positions=True)
     assert full.shape == (1, L, vocab) and relerr(full, ref) < tol
     assert relerr(full[:, -1:], last) < (1e-5 if dtype == torch.float32 else 1e-2)   # same row; cuBLAS picks another kernel for M = 1
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_pyramid_drop_against_reference_golden(dtype, tol):
+    """TransV / pyramid-drop between layers (one uniform and two attention-ranked stages) against the
+    reference's own NemotronHModel.forward with use_pdrop (tests/golden/pdrop_uni_attn_attn.npz): 145 -> 55 tokens."""
+    import timeviper_b200 as tv
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pdrop_uni_attn_attn.npz"))
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pre, V, post = [int(v) for v in z["dims"]]
+    pattern = str(z["pattern"])
+    cfg = tv.Mamba2Config(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, n_groups=G, ssm_state_size=N,
+                          chunk_size=Q, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                          num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd, intermediate_size_mlp=mlp,
+                          vocab_size=100)
+    model = tv.HybridPrefillStack(cfg)
+    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type")
+    model.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files if k not in skip}, strict=True)
+    model = model.to(dtype).cuda().eval()
+    x = torch.from_numpy(z["inputs_embeds"]).to(dtype).cuda()
+    pd = dict(pdrop_type=str(z["pdrop_type"]), first_vision_token_position=pre, num_vision_tokens=V, text_prompt_len=pre + post)
+    out = model(inputs_embeds=x, pdrop=pd)
+    ref = torch.from_numpy(z["last_hidden_state"])
+    assert out.shape == ref.shape == (1, pre + int(V * 0.25) + post, hidden)
+    if dtype == torch.float32:
+        assert relerr(out, ref) < tol
+    else:
+        # bf16 may rank two near-tied vision tokens the other way round, which swaps whole rows: compare the rows that
+        # both runs kept (text and prefix rows are always kept) -- and most vision rows must agree
+        close = ((out.float().cpu() - ref).abs().amax(-1) / ref.abs().max()) < tol
+        assert bool(close[0, :pre].all()) and bool(close[0, -post:].all()) and float(close.float().mean()) > 0.8

@@ -181,3 +181,19 @@ def test_causal_lm_logits_oracle_matches_reference_golden():
     ref = torch.from_numpy(z["logits"])
     assert logits.shape == ref.shape == (1, L, vocab) and logits.dtype == torch.float32
     assert float((logits - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+def test_pdrop_oracle_matches_reference_golden():
+    """TransV / pyramid-drop (uniform + two attention-ranked stages) through the reference's own NemotronHModel.forward."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pdrop_uni_attn_attn.npz"))
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pre, V, post = [int(v) for v in z["dims"]]
+    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type")
+    sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in skip}
+    out = R.hybrid_forward_ref(sd, torch.from_numpy(z["inputs_embeds"]), pattern=str(z["pattern"]), num_heads=H, head_dim=P,
+                               n_groups=G, ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd,
+                               pdrop=dict(pdrop_type=str(z["pdrop_type"]), first_vision_token_position=pre,
+                                          num_vision_tokens=V, text_prompt_len=pre + post))
+    ref = torch.from_numpy(z["last_hidden_state"])
+    assert out.shape == ref.shape == (1, pre + int(V * 0.25) + post, hidden)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-5

@@ -85,6 +85,45 @@ class HybridBlock(nn.Module):
         return residual + h
 
 
+def parse_pdrop_type(pdrop_type):
+    """'type_layer_ratio-...' -> (types, layers, ratios with a leading 1)   (modeling_nano.py:1469-1477; the default
+    schedule of evaluate.py:167-172 is 'uni_14_0.8-attn_21_0.6-attn_30_0.4-attn_39_0.2')."""
+    parts = [t.split("_") for t in pdrop_type.split("-")]
+    if not all(len(t) == 3 for t in parts):
+        raise ValueError("pdrop_type should be like 'type_layernum_ratio-...'")
+    return [t[0] for t in parts], [int(t[1]) for t in parts], [1.0] + [float(t[2]) for t in parts]
+
+
+@torch.no_grad()
+def pdrop_select(h, stage, kind, ratios, attn, vision_index, num_vision_tokens, text_prompt_len):
+    """TransV / pyramid-drop token selection for inference, one sample (``pdrop_no_pack``, modeling_nano.py:1779-1988):
+    sorted sequence indices of the vision tokens that survive stage ``stage`` and the index of the first token after
+    the vision block.  h: (L, hidden), the hidden states entering the layer (NOT normed, as in the reference :1821-1836).
+
+    'uni': evenly spaced (:1950-1957).  'attn': attention of the LAST prompt token over the sequence, with this attention
+    layer's q/k projections, softmax in fp32, mean over heads, top-k among the vision tokens (:1917-1947).  The reference
+    projects q for every position and builds an (L, L) mask; only one query row is ever read, so this computes that row:
+    one (1 x hidden) q GEMV, the k projection of the positions up to the query, and heads x L scores."""
+    image_tokens = int(num_vision_tokens * ratios[stage])
+    keep = int(num_vision_tokens * ratios[stage + 1])
+    if "attn" in kind:
+        if attn is None:
+            raise ValueError("an attention-ranked drop must sit on an attention layer (modeling_nano.py:1824)")
+        pq = text_prompt_len + image_tokens - 1
+        nh, nkv, d = attn.num_heads, attn.num_key_value_heads, attn.head_dim
+        q = attn.q_proj(h[pq:pq + 1]).view(nh, 1, d)
+        k = attn.k_proj(h[:pq + 1]).view(pq + 1, nkv, d).transpose(0, 1)                  # keys the causal row can see
+        k = k.repeat_interleave(nh // nkv, dim=0)
+        w = torch.softmax((q @ k.transpose(1, 2)) / (d ** 0.5), dim=-1, dtype=torch.float32).to(h.dtype)   # (nh, 1, pq+1)
+        w = w.mean(0)[0, vision_index:vision_index + image_tokens]
+        top = w.topk(keep).indices
+    elif "uni" in kind:
+        top = torch.linspace(0, image_tokens - 1, keep, dtype=torch.long).to(h.device)     # on the host, as the reference's
+    else:
+        raise NotImplementedError(kind)
+    return (top + vision_index).sort().values, vision_index + image_tokens
+
+
 class HybridPrefillStack(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -96,8 +135,12 @@ class HybridPrefillStack(nn.Module):
         self.norm_f = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
 
     @torch.no_grad()
-    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None):
-        """Prefill: (b, L) token ids or (b, L, hidden) embeddings -> last hidden states (b, L, hidden) after ``norm_f``.
+    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, pdrop=None):
+        """Prefill: (b, L) token ids or (b, L, hidden) embeddings -> last hidden states (b, L', hidden) after ``norm_f``.
+        ``pdrop`` (the reference's ``train_pdrop_args`` + ``config.pdrop_type``) = dict(pdrop_type=
+        'uni_14_0.8-attn_21_0.6-...', first_vision_token_position, num_vision_tokens, text_prompt_len): TransV /
+        pyramid-drop of vision tokens before the listed layers (modeling_nano.py:1634-1666; batch 1, ``no_merge``), so the
+        layers after a stage see L' < L tokens: [tokens before the video | surviving vision tokens | text].
         ``cache_params`` (reference cache interface) receives the conv / SSM states of every Mamba-2 layer.
         Limits (stated, not hidden): no ``attention_mask`` (batch 1 or unpadded batches only) and the attention layers do
         not write a KV cache, so this stack prefills and scores the last position; token-by-token decode after it needs
@@ -106,7 +149,18 @@ class HybridPrefillStack(nn.Module):
             raise ValueError("exactly one of input_ids / inputs_embeds")
         h = self.embeddings(input_ids) if inputs_embeds is None else inputs_embeds
         pos = torch.arange(h.shape[1])          # on the HOST: the mixer branches on cache_position[0] > 0 (no device sync)
-        for layer in self.layers:
+        if pdrop is not None:
+            if h.shape[0] != 1:
+                raise NotImplementedError("pyramid-drop is wired for batch 1 (the reference's inference path)")
+            kinds, drop_layers, ratios = parse_pdrop_type(pdrop["pdrop_type"])
+        for i, layer in enumerate(self.layers):
+            if pdrop is not None and i in drop_layers:
+                st = drop_layers.index(i)
+                vi = pdrop["first_vision_token_position"]
+                top, start = pdrop_select(h[0], st, kinds[st], ratios, layer.mixer if layer.block_type == "attention" else None,
+                                          vi, pdrop["num_vision_tokens"], pdrop["text_prompt_len"])
+                h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)                 # :1981-1988
+                pos = torch.arange(h.shape[1])
             h = layer(h, cache_params=cache_params, cache_position=pos)
         return self.norm_f(h)
 
@@ -127,8 +181,8 @@ class HybridCausalLM(nn.Module):
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
 
     @torch.no_grad()
-    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, all_positions=False):
-        h = self.backbone(input_ids=input_ids, inputs_embeds=inputs_embeds, cache_params=cache_params)
+    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, all_positions=False, pdrop=None):
+        h = self.backbone(input_ids=input_ids, inputs_embeds=inputs_embeds, cache_params=cache_params, pdrop=pdrop)
         if not all_positions:
             h = h[:, -1:]
         return self.lm_head(h.to(self.lm_head.weight.dtype)).float()
