@@ -483,24 +483,33 @@ def run_ours(args):
 
 
 def run_hybrid(args):
-    """BASELINE.json configs[3]: prefill of the 56-layer Nanov2-9B-shaped hybrid LM (random init) over 5K frames of synthetic
-    video tokens (81,920 tokens), Mamba-2 layers on this package's kernels, attention on library SDPA, MLP and projections
-    on cuBLAS, last-token lm_head.  One GPU.  A step = one whole prefill from token embeddings resident in HBM to the fp32
-    logits of the last position."""
+    """BASELINE.json configs[3] / [4]: prefill of the 56-layer Nanov2-9B-shaped hybrid LM (random init) over synthetic video
+    tokens, Mamba-2 layers on this package's kernels, attention on library SDPA, MLP and projections on cuBLAS, last-token
+    lm_head.  A step = one whole prefill from token embeddings resident in HBM to the fp32 logits of the last position.
+    --workload hybrid9b      : 5K frames (81,920 tokens), no token drop                                   (configs[3])
+    --workload hybrid9b-pdrop: 10K frames (163,840 tokens + 64 text), TransV / pyramid-drop at layers 14/21/30/39 with the
+                               reference's default schedule (evaluate.py:167-172)                          (configs[4])
+    N > 1: N independent replicas, ONE sample per GPU (weak scaling, no collective on the data path): the layer loop that
+    shards one sample over several GPUs is not built, so configs[4]'s "batch 4 across 8 GPUs" runs here as 8 x batch 1."""
     import timeviper_b200 as tv
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus != 1:
-        if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps({"metric": "hybrid_prefill_tokens_per_s", "unavailable": "the hybrid stack is single-GPU (the sequence-sharded layer loop is not built)"}))
-        return
-    torch.cuda.set_device(0)
-    L = args.seqlen if args.seqlen != 131072 else 81920
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    drop = args.workload == "hybrid9b-pdrop"
+    text = 64 if drop else 0
+    L = args.seqlen if args.seqlen != 131072 else (163840 + text if drop else 81920)
     cfg = tv.Mamba2Config.nanov2_9b_hybrid()
-    torch.manual_seed(0)
+    torch.manual_seed(rank)
     with torch.device("cuda"):
         model = tv.HybridCausalLM(cfg).to(torch.bfloat16).eval()
     x = torch.randn(1, L, cfg.hidden_size, device="cuda").to(torch.bfloat16)
-    share = {}
-    ev = []
+    pd = dict(pdrop_type="uni_14_0.8-attn_21_0.6-attn_30_0.4-attn_39_0.2", first_vision_token_position=0,
+              num_vision_tokens=L - text, text_prompt_len=text) if drop else None
+    run = lambda inp: model(inputs_embeds=inp, pdrop=pd)
+    share, ev = {}, []
 
     def pre(m, a):
         e = torch.cuda.Event(enable_timing=True); e.record(); m._e0 = e
@@ -508,23 +517,20 @@ def run_hybrid(args):
     def post(m, a, o):
         e = torch.cuda.Event(enable_timing=True); e.record(); ev.append((m.block_type, m._e0, e))
     for _ in range(max(args.warmup, 1)):
-        logits = model(inputs_embeds=x)
+        logits = run(x)
     torch.cuda.synchronize()
-    sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); time.sleep(0.3)
     n0 = tv.launch_count()
     t0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        logits = model(inputs_embeds=x)
-    e1.record(); torch.cuda.synchronize()
-    clocks = sampler.stop(t0, time.time())
+    ms = time_region(lambda: run(x), args.steps, dist_on)
+    clocks = sampler.stop(t0, time.time()) if rank == 0 else None
     launches = tv.launch_count() - n0
-    ms = e0.elapsed_time(e1) / args.steps
     hooks = []
     for layer in model.backbone.layers:
         hooks += [layer.register_forward_pre_hook(pre), layer.register_forward_hook(post)]
-    logits = model(inputs_embeds=x); torch.cuda.synchronize()
+    logits = run(x); torch.cuda.synchronize()
     for kind, a, b in ev:
         share[kind] = share.get(kind, 0.0) + a.elapsed_time(b)
     for hk in hooks:
@@ -533,27 +539,35 @@ def run_hybrid(args):
     hx = torch.empty(x.shape, dtype=x.dtype).pin_memory(); hx.copy_(x.cpu())
     hl = torch.empty(logits.shape, dtype=logits.dtype).pin_memory()
     k = max(1, min(args.e2e_steps, 3))
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(k):
-        hl.copy_(model(inputs_embeds=hx.cuda(non_blocking=True)), non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / k * 1e3
-    pat = cfg.hybrid_override_pattern
-    print(json.dumps({
-        "metric": "hybrid_prefill_tokens_per_s", "value": L / ms * 1e3, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-        "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Nanov2-9B-shaped hybrid LM prefill (BASELINE.json configs[3]): 56 layers "
-                               f"({pat.count('M')} Mamba-2 / {pat.count('*')} attention / {pat.count('-')} MLP), random init, batch 1, "
-                               "last-token lm_head", "seqlen": L, "parallelism": "single",
-                   "params_B": round(sum(p.numel() for p in model.parameters()) / 1e9, 2),
-                   "l2": "activations (0.7 GB per layer boundary, 3.7 GB in_proj output) >> L2 (126 MB); no flush needed"},
-        "e2e": {"value": L / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "steps": k, "h2d_bytes_per_step": hx.numel() * 2,
-                "d2h_bytes_per_step": hl.numel() * 4, "api": "HybridCausalLM.forward(inputs_embeds) from pinned host embeddings to host logits"},
-        "gpu_launches": launches, "clocks": clocks,
-        "layer_time_share_ms": {k2: round(v, 1) for k2, v in sorted(share.items())},
-        "finite": bool(torch.isfinite(logits).all()),
-    }))
+
+    def e2e():
+        hl.copy_(run(hx.cuda(non_blocking=True)), non_blocking=True)
+    e2e_ms = time_region(e2e, k, dist_on)
+    finite = bool(torch.isfinite(logits).all())
+    if dist_on:
+        fin = torch.tensor([1.0 if finite else 0.0], device="cuda")
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        finite = bool(fin.item() > 0)
+    if rank == 0:
+        pat = cfg.hybrid_override_pattern
+        print(json.dumps({
+            "metric": "hybrid_prefill_tokens_per_s", "value": world * L / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Nanov2-9B-shaped hybrid LM prefill (BASELINE.json configs[%d]): 56 layers " % (4 if drop else 3) +
+                                   f"({pat.count('M')} Mamba-2 / {pat.count('*')} attention / {pat.count('-')} MLP), random init, "
+                                   "last-token lm_head" + (", TransV / pyramid-drop " + pd["pdrop_type"] if drop else ""),
+                       "seqlen": L, "global_batch": world, "parallelism": "single" if world == 1 else f"{world} replicas x batch 1",
+                       "params_B": round(sum(p.numel() for p in model.parameters()) / 1e9, 2),
+                       "l2": "activations (GBs per layer) >> L2 (126 MB); no flush needed"},
+            "e2e": {"value": world * L / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "steps": k, "h2d_bytes_per_step": hx.numel() * 2,
+                    "d2h_bytes_per_step": hl.numel() * 4, "api": "HybridCausalLM.forward(inputs_embeds[, pdrop]) from pinned host embeddings to host logits"},
+            "gpu_launches": launches, "clocks": clocks,
+            "layer_time_share_ms": {k2: round(v, 1) for k2, v in sorted(share.items())},
+            "finite": finite,
+        }))
+    if dist_on:
+        dist.destroy_process_group()
 
 
 def main():
@@ -570,10 +584,10 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (default: all host cores)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="back-to-back seconds for the sustained step time")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the three kernels eagerly instead of one CUDA graph")
-    ap.add_argument("--workload", default="mixer", choices=["mixer", "hybrid9b"],
-                    help="mixer: the BASELINE metric (default); hybrid9b: BASELINE.json configs[3], its own JSON line")
+    ap.add_argument("--workload", default="mixer", choices=["mixer", "hybrid9b", "hybrid9b-pdrop"],
+                    help="mixer: the BASELINE metric (default); hybrid9b / hybrid9b-pdrop: BASELINE.json configs[3] / [4], own JSON line")
     args = ap.parse_args()
-    if args.workload == "hybrid9b" and args.impl == "ours":
+    if args.workload != "mixer" and args.impl == "ours":
         run_hybrid(args)
     elif args.impl == "reference":
         run_reference(args)
