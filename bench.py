@@ -489,8 +489,10 @@ def run_hybrid(args):
     --workload hybrid9b      : 5K frames (81,920 tokens), no token drop                                   (configs[3])
     --workload hybrid9b-pdrop: 10K frames (163,840 tokens + 64 text), TransV / pyramid-drop at layers 14/21/30/39 with the
                                reference's default schedule (evaluate.py:167-172)                          (configs[4])
-    N > 1: N independent replicas, ONE sample per GPU (weak scaling, no collective on the data path): the layer loop that
-    shards one sample over several GPUs is not built, so configs[4]'s "batch 4 across 8 GPUs" runs here as 8 x batch 1."""
+    N > 1: N / S replicas of ONE sample each, every sample sharded over S = --shard GPUs (default 1: N independent replicas,
+    no collective on the data path).  With S > 1 the layer loop runs sequence-sharded (Mamba-2 layers: conv halo + boundary
+    states; attention layers: K/V all-gather; hybrid9b only -- a pyramid-drop changes the shard lengths), so BASELINE
+    configs[4]'s "batch 4 across 8 GPUs" is `--gpus 8 --shard 2` without the drop, or 8 x batch 1 with it."""
     import timeviper_b200 as tv
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -499,16 +501,25 @@ def run_hybrid(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     drop = args.workload == "hybrid9b-pdrop"
+    S = max(1, args.shard)
+    if world % S or (S > 1 and drop):
+        raise SystemExit("bench.py: --shard must divide the number of GPUs and is not combined with the pyramid-drop workload")
+    grp = None
+    if S > 1:       # process groups of S consecutive ranks; every rank creates all of them (collective call)
+        for g0 in range(0, world, S):
+            gnew = dist.new_group(list(range(g0, g0 + S)))
+            if g0 <= rank < g0 + S:
+                grp = gnew
     text = 64 if drop else 0
     L = args.seqlen if args.seqlen != 131072 else (163840 + text if drop else 81920)
     cfg = tv.Mamba2Config.nanov2_9b_hybrid()
-    torch.manual_seed(rank)
+    torch.manual_seed(rank // S)                  # the ranks of one sample hold the same weights
     with torch.device("cuda"):
         model = tv.HybridCausalLM(cfg).to(torch.bfloat16).eval()
-    x = torch.randn(1, L, cfg.hidden_size, device="cuda").to(torch.bfloat16)
+    x = torch.randn(1, L // S, cfg.hidden_size, device="cuda").to(torch.bfloat16)     # this rank's shard of its sample
     pd = dict(pdrop_type="uni_14_0.8-attn_21_0.6-attn_30_0.4-attn_39_0.2", first_vision_token_position=0,
               num_vision_tokens=L - text, text_prompt_len=text) if drop else None
-    run = lambda inp: model(inputs_embeds=inp, pdrop=pd)
+    run = lambda inp: model(inputs_embeds=inp, pdrop=pd, group=grp)
     share, ev = {}, []
 
     def pre(m, a):
@@ -551,16 +562,17 @@ def run_hybrid(args):
     if rank == 0:
         pat = cfg.hybrid_override_pattern
         print(json.dumps({
-            "metric": "hybrid_prefill_tokens_per_s", "value": world * L / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": "hybrid_prefill_tokens_per_s", "value": (world // S) * L / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "Nanov2-9B-shaped hybrid LM prefill (BASELINE.json configs[%d]): 56 layers " % (4 if drop else 3) +
                                    f"({pat.count('M')} Mamba-2 / {pat.count('*')} attention / {pat.count('-')} MLP), random init, "
                                    "last-token lm_head" + (", TransV / pyramid-drop " + pd["pdrop_type"] if drop else ""),
-                       "seqlen": L, "global_batch": world, "parallelism": "single" if world == 1 else f"{world} replicas x batch 1",
+                       "seqlen": L, "global_batch": world // S,
+                       "parallelism": "single" if world == 1 else f"{world // S} replicas x batch 1" + (f", each sequence-sharded over {S} GPUs" if S > 1 else ""),
                        "params_B": round(sum(p.numel() for p in model.parameters()) / 1e9, 2),
                        "l2": "activations (GBs per layer) >> L2 (126 MB); no flush needed"},
-            "e2e": {"value": world * L / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "steps": k, "h2d_bytes_per_step": hx.numel() * 2,
+            "e2e": {"value": (world // S) * L / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms, "steps": k, "h2d_bytes_per_step": hx.numel() * 2,
                     "d2h_bytes_per_step": hl.numel() * 4, "api": "HybridCausalLM.forward(inputs_embeds[, pdrop]) from pinned host embeddings to host logits"},
             "gpu_launches": launches, "clocks": clocks,
             "layer_time_share_ms": {k2: round(v, 1) for k2, v in sorted(share.items())},
@@ -584,6 +596,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (default: all host cores)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="back-to-back seconds for the sustained step time")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the three kernels eagerly instead of one CUDA graph")
+    ap.add_argument("--shard", type=int, default=1, help="hybrid workloads: GPUs per sample (sequence-sharded layer loop)")
     ap.add_argument("--workload", default="mixer", choices=["mixer", "hybrid9b", "hybrid9b-pdrop"],
                     help="mixer: the BASELINE metric (default); hybrid9b / hybrid9b-pdrop: BASELINE.json configs[3] / [4], own JSON line")
     args = ap.parse_args()

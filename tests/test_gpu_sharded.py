@@ -81,3 +81,61 @@ def test_sharded_equals_unsharded_nccl(dtype_name, tol):
         assert r["err"] < tol, r
         if r["rank"] == world - 1:
             assert r["ssm_err"] < tol and r["conv_equal"], r
+
+
+def _hybrid_worker(rank, world, port, L, dtype_name, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import timeviper_b200 as tv
+        dtype = getattr(torch, dtype_name)
+        torch.manual_seed(321)
+        pattern = "M-M*M-*M"
+        cfg = tv.Mamba2Config(hidden_size=256, mamba_num_heads=16, mamba_head_dim=80, n_groups=2, ssm_state_size=128,
+                              chunk_size=128, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                              num_attention_heads=8, num_key_value_heads=2, head_dim=64, intermediate_size_mlp=512, vocab_size=1000)
+        model = tv.HybridCausalLM(cfg)
+        with torch.no_grad():
+            for layer in model.backbone.layers:
+                if layer.block_type == "mamba":
+                    layer.mixer.reset_parameters_like_reference()
+                    layer.mixer.A_log.copy_(torch.log(torch.rand(16) * 0.5 + 0.01))
+                    layer.mixer.D.copy_(torch.randn(16))
+        model = model.to(dtype).cuda().eval()
+        ids = torch.randint(0, 1000, (1, L)).cuda()
+        sl = slice(rank * L // world, (rank + 1) * L // world)
+        with torch.no_grad():
+            ref_h = model.backbone(input_ids=ids)
+            ref_logits = model(input_ids=ids)
+            h = model.backbone(input_ids=ids[:, sl], group=dist.group.WORLD)
+            logits = model(input_ids=ids[:, sl], group=dist.group.WORLD)
+        torch.cuda.synchronize()
+        q.put({"rank": rank, "err": float((h.float() - ref_h[:, sl].float()).abs().max() / ref_h.float().abs().max()),
+               "logit_err": float((logits - ref_logits).abs().max() / ref_logits.abs().max())})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype_name,tol", [("bfloat16", 3e-2), ("float32", 1e-4)])
+def test_sharded_hybrid_stack_equals_unsharded_nccl(dtype_name, tol):
+    """SURVEY.md 8f row f1, sharded: the hybrid layer loop with ONE sequence sharded over the GPUs (Mamba-2 layers on the
+    sharded mixer, attention layers with a K/V all-gather, last-token logits broadcast from the last rank) equals the same
+    model on one GPU."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    L = 512 * world
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, world, port, L, dtype_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in results:
+        assert r["err"] < tol and r["logit_err"] < tol, r

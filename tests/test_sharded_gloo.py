@@ -105,3 +105,59 @@ def test_sharded_equals_unsharded_gloo(world, L):
             assert r["ssm_err"] < 1e-11 and r["conv_equal"], r
         else:
             assert r["cache_untouched"], r
+
+
+def _hybrid_worker(rank, world, port, L, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import timeviper_b200 as tv
+        torch.manual_seed(11)
+        pattern = "M*-M*"
+        cfg = tv.Mamba2Config(hidden_size=32, mamba_num_heads=4, mamba_head_dim=8, n_groups=2, ssm_state_size=16,
+                              chunk_size=32, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                              num_attention_heads=4, num_key_value_heads=2, head_dim=8, intermediate_size_mlp=48, vocab_size=50)
+        model = tv.HybridCausalLM(cfg).double()
+        with torch.no_grad():
+            for layer in model.backbone.layers:
+                if layer.block_type == "mamba":
+                    layer.mixer.A_log.copy_(torch.log(torch.rand(4) * 3 + 0.05))
+                    layer.mixer.dt_bias.copy_(torch.randn(4) * 0.5 - 2.0)
+                    layer.mixer.D.copy_(torch.randn(4))
+        x = torch.randn(1, L, 32, dtype=torch.float64)
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        bb = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+        ref_h = R.hybrid_forward_ref(bb, x, pattern=pattern, num_heads=4, head_dim=8, n_groups=2, ssm_state_size=16,
+                                     chunk_size=32, attn_heads=4, kv_heads=2, attn_head_dim=8, dtype=torch.float64)
+        ref_logits = torch.nn.functional.linear(ref_h[:, -1:], sd["lm_head.weight"])
+        sl = slice(rank * L // world, (rank + 1) * L // world)
+        with torch.no_grad():
+            h = model.backbone(inputs_embeds=x[:, sl], group=dist.group.WORLD, mixer_ops=_oracle_ops())
+            logits = model.lm_head(h[:, -1:])
+        res = {"rank": rank, "err": float((h - ref_h[:, sl]).abs().max() / ref_h.abs().max())}
+        if rank == world - 1:
+            res["logit_err"] = float((logits - ref_logits).abs().max() / ref_logits.abs().max())
+        out_q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,L", [(2, 128), (4, 192), (3, 99)])
+def test_sharded_hybrid_stack_equals_unsharded_gloo(world, L):
+    """Sequence-sharded hybrid layer loop (Mamba-2 layers: halo + boundary states; attention layers: K/V all-gather with a
+    lower-right causal mask; MLP / norms token-local) against the unsharded oracle stack, fp64, gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, world, port, L, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in results:       # the stack's RMSNorm takes its statistics in fp32 (as the reference's does): 1e-7, not 1e-11
+        assert r["err"] < 1e-6, r
+        if r["rank"] == world - 1:
+            assert r["logit_err"] < 1e-6, r

@@ -10,6 +10,7 @@ Parameter names are the reference's (``embeddings``, ``layers.N.norm``, ``layers
 kept here so that a whole prefill can be checked against the reference (tests/golden/hybrid_*.npz) and timed.
 Deliberately NOT mirrored: the per-layer ``isnan().any()`` host sync (:1690) -- it serialises the GPU every layer."""
 import torch
+import torch.distributed as dist
 from torch import nn
 
 from .mixer import Mamba2MixerPrefill
@@ -52,6 +53,31 @@ class Attention(nn.Module):
         return self.o_proj(o.transpose(1, 2).reshape(b, L, self.num_heads * self.head_dim))
 
 
+def sharded_attention_forward(attn, hidden_states, group=None):
+    """Causal attention of a sequence-sharded layer: rank r holds tokens [r*Ls, (r+1)*Ls) (equal shards).  K and V of every
+    rank are all-gathered (GQA: 2 x kv_heads x head_dim values per token, 4 KB at the 9B shape -- 1/10 of the hidden state),
+    each rank attends its queries over the keys of ranks <= r with a LOWER-RIGHT aligned causal mask (its queries are the
+    last Ls positions of that key range), which library SDPA takes without materialising a mask.  The work per rank grows
+    with r (causal); a zig-zag split would balance it but breaks the contiguous shards the Mamba-2 layers need."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b, L, _ = hidden_states.shape
+    nh, nkv, d = attn.num_heads, attn.num_key_value_heads, attn.head_dim
+    q = attn.q_proj(hidden_states).view(b, L, nh, d).transpose(1, 2)
+    kv = torch.stack([attn.k_proj(hidden_states), attn.v_proj(hidden_states)]).contiguous()        # (2, b, L, nkv*d)
+    gathered = torch.empty((world,) + tuple(kv.shape), dtype=kv.dtype, device=kv.device)
+    dist.all_gather_into_tensor(gathered.view(-1), kv.view(-1), group=group)
+    gathered = gathered[:rank + 1]                                                                   # keys this rank may see
+    k = gathered[:, 0].permute(1, 0, 2, 3).reshape(b, (rank + 1) * L, nkv, d).transpose(1, 2)
+    v = gathered[:, 1].permute(1, 0, 2, 3).reshape(b, (rank + 1) * L, nkv, d).transpose(1, 2)
+    if hidden_states.is_cuda:
+        from torch.nn.attention.bias import causal_lower_right
+        mask = causal_lower_right(L, (rank + 1) * L)
+    else:       # CPU (gloo tests of the host logic): the same mask, materialised
+        mask = torch.ones(L, (rank + 1) * L, dtype=torch.bool).tril(diagonal=rank * L)
+    o = nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask, enable_gqa=nh != nkv)
+    return attn.o_proj(o.transpose(1, 2).reshape(b, L, nh * d))
+
+
 class MLP(nn.Module):
     def __init__(self, config, layer_idx=None):
         super().__init__()
@@ -75,11 +101,20 @@ class HybridBlock(nn.Module):
         self.norm = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
         self.mixer = {"mamba": Mamba2MixerPrefill, "attention": Attention, "mlp": MLP}[self.block_type](config, layer_idx)
 
-    def forward(self, hidden_states, cache_params=None, cache_position=None):
+    def forward(self, hidden_states, cache_params=None, cache_position=None, group=None, mixer_ops=None):
+        """group: the sequence is sharded contiguously over this process group (equal shards, rank order = token order)."""
         residual = hidden_states.to(torch.float32) if self.residual_in_fp32 else hidden_states
         h = self.norm(hidden_states.to(self.norm.weight.dtype))
+        sharded = group is not None and dist.get_world_size(group) > 1
         if self.block_type == "mamba":
-            h = self.mixer(h, cache_params=cache_params, cache_position=cache_position)
+            if sharded:
+                from .sharded import sharded_mixer_forward
+                kw = {} if mixer_ops is None else {"ops": mixer_ops}
+                h = sharded_mixer_forward(self.mixer, h, group=group, cache_params=cache_params, **kw)
+            else:
+                h = self.mixer(h, cache_params=cache_params, cache_position=cache_position)
+        elif self.block_type == "attention" and sharded:
+            h = sharded_attention_forward(self.mixer, h, group)
         else:
             h = self.mixer(h)
         return residual + h
@@ -135,12 +170,17 @@ class HybridPrefillStack(nn.Module):
         self.norm_f = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
 
     @torch.no_grad()
-    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, pdrop=None):
+    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, pdrop=None, group=None, mixer_ops=None):
         """Prefill: (b, L) token ids or (b, L, hidden) embeddings -> last hidden states (b, L', hidden) after ``norm_f``.
         ``pdrop`` (the reference's ``train_pdrop_args`` + ``config.pdrop_type``) = dict(pdrop_type=
         'uni_14_0.8-attn_21_0.6-...', first_vision_token_position, num_vision_tokens, text_prompt_len): TransV /
         pyramid-drop of vision tokens before the listed layers (modeling_nano.py:1634-1666; batch 1, ``no_merge``), so the
         layers after a stage see L' < L tokens: [tokens before the video | surviving vision tokens | text].
+        ``group`` (a torch.distributed process group of more than one rank): the inputs are this rank's contiguous shard of
+        ONE sequence (equal shards, rank order = token order) and so is the result; Mamba-2 layers run
+        ``sharded_mixer_forward`` (conv halo + boundary-state exchange), attention layers all-gather K / V
+        (``sharded_attention_forward``), everything else is token-local.  Not combined with ``pdrop`` (a drop changes the
+        shard lengths and would need a re-balancing step).
         ``cache_params`` (reference cache interface) receives the conv / SSM states of every Mamba-2 layer.
         Limits (stated, not hidden): no ``attention_mask`` (batch 1 or unpadded batches only) and the attention layers do
         not write a KV cache, so this stack prefills and scores the last position; token-by-token decode after it needs
@@ -149,7 +189,10 @@ class HybridPrefillStack(nn.Module):
             raise ValueError("exactly one of input_ids / inputs_embeds")
         h = self.embeddings(input_ids) if inputs_embeds is None else inputs_embeds
         pos = torch.arange(h.shape[1])          # on the HOST: the mixer branches on cache_position[0] > 0 (no device sync)
+        sharded = group is not None and dist.get_world_size(group) > 1
         if pdrop is not None:
+            if sharded:
+                raise NotImplementedError("pyramid-drop over a sequence-sharded stack is not built")
             if h.shape[0] != 1:
                 raise NotImplementedError("pyramid-drop is wired for batch 1 (the reference's inference path)")
             kinds, drop_layers, ratios = parse_pdrop_type(pdrop["pdrop_type"])
@@ -161,7 +204,7 @@ class HybridPrefillStack(nn.Module):
                                           vi, pdrop["num_vision_tokens"], pdrop["text_prompt_len"])
                 h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)                 # :1981-1988
                 pos = torch.arange(h.shape[1])
-            h = layer(h, cache_params=cache_params, cache_position=pos)
+            h = layer(h, cache_params=cache_params, cache_position=pos, group=group if sharded else None, mixer_ops=mixer_ops)
         return self.norm_f(h)
 
 
@@ -181,8 +224,13 @@ class HybridCausalLM(nn.Module):
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
 
     @torch.no_grad()
-    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, all_positions=False, pdrop=None):
-        h = self.backbone(input_ids=input_ids, inputs_embeds=inputs_embeds, cache_params=cache_params, pdrop=pdrop)
+    def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, all_positions=False, pdrop=None, group=None):
+        """With ``group`` (sequence-sharded prefill): every rank returns the logits of the sequence's LAST position (computed
+        on the last rank and broadcast); ``all_positions`` then gives the logits of this rank's shard."""
+        h = self.backbone(input_ids=input_ids, inputs_embeds=inputs_embeds, cache_params=cache_params, pdrop=pdrop, group=group)
         if not all_positions:
             h = h[:, -1:]
-        return self.lm_head(h.to(self.lm_head.weight.dtype)).float()
+        logits = self.lm_head(h.to(self.lm_head.weight.dtype)).float()
+        if group is not None and dist.get_world_size(group) > 1 and not all_positions:
+            dist.broadcast(logits, src=dist.get_global_rank(group, dist.get_world_size(group) - 1), group=group)
+        return logits
