@@ -53,6 +53,37 @@ class Attention(nn.Module):
         return self.o_proj(o.transpose(1, 2).reshape(b, L, self.num_heads * self.head_dim))
 
 
+_two_part_ok = True
+
+
+def _two_part_attention(q, k, v, L, rep):
+    """Lower-right causal attention of this rank's L queries over (r+1)*L keys as TWO library calls on their fast paths --
+    full attention over the r*L keys of the earlier ranks and square causal attention over this rank's own keys -- merged
+    through the log-sum-exp each call returns.  (A lower-right CausalBias makes PyTorch pick the FlashAttention-2 backend,
+    which on B200 is ~3x slower than the cuDNN one it uses for plain causal attention: 130 ms against 42 ms of work at
+    40K tokens per rank.)  Uses the private aten cuDNN SDPA op for the LSE output; returns None if it is not available, and
+    the caller falls back to the single masked call."""
+    global _two_part_ok
+    if not _two_part_ok:
+        return None
+    try:
+        op = torch.ops.aten._scaled_dot_product_cudnn_attention
+        kp, vp = k[:, :, :-L], v[:, :, :-L]
+        ko, vo = k[:, :, -L:], v[:, :, -L:]
+        if rep > 1:       # the private op has no enable_gqa: expand the KV heads (views, no copy)
+            ex = lambda t: t.unsqueeze(2).expand(-1, -1, rep, -1, -1).reshape(t.shape[0], t.shape[1] * rep, t.shape[2], t.shape[3])
+            kp, vp, ko, vo = ex(kp), ex(vp), ex(ko), ex(vo)
+        oa, la = op(q, kp, vp, None, True, 0.0, False)[:2]
+        ob, lb = op(q, ko, vo, None, True, 0.0, True)[:2]
+        la, lb = la.float().reshape(la.shape[0], la.shape[1], -1, 1), lb.float().reshape(lb.shape[0], lb.shape[1], -1, 1)
+        m = torch.maximum(la, lb)
+        wa, wb = torch.exp(la - m), torch.exp(lb - m)
+        return ((oa.float() * wa + ob.float() * wb) / (wa + wb)).to(q.dtype)
+    except Exception:       # op missing / shape unsupported on this build: one-time fallback
+        _two_part_ok = False
+        return None
+
+
 def sharded_attention_forward(attn, hidden_states, group=None):
     """Causal attention of a sequence-sharded layer: rank r holds tokens [r*Ls, (r+1)*Ls) (equal shards).  K and V of every
     rank are all-gathered (GQA: 2 x kv_heads x head_dim values per token, 4 KB at the 9B shape -- 1/10 of the hidden state),
@@ -69,12 +100,16 @@ def sharded_attention_forward(attn, hidden_states, group=None):
     gathered = gathered[:rank + 1]                                                                   # keys this rank may see
     k = gathered[:, 0].permute(1, 0, 2, 3).reshape(b, (rank + 1) * L, nkv, d).transpose(1, 2)
     v = gathered[:, 1].permute(1, 0, 2, 3).reshape(b, (rank + 1) * L, nkv, d).transpose(1, 2)
-    if hidden_states.is_cuda:
-        from torch.nn.attention.bias import causal_lower_right
-        mask = causal_lower_right(L, (rank + 1) * L)
-    else:       # CPU (gloo tests of the host logic): the same mask, materialised
-        mask = torch.ones(L, (rank + 1) * L, dtype=torch.bool).tril(diagonal=rank * L)
-    o = nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask, enable_gqa=nh != nkv)
+    o = None
+    if hidden_states.is_cuda and rank > 0 and q.dtype in (torch.bfloat16, torch.float16):   # the cuDNN op is half-precision only
+        o = _two_part_attention(q, k, v, L, nh // nkv)
+    if o is None:
+        if hidden_states.is_cuda:
+            from torch.nn.attention.bias import causal_lower_right
+            mask = causal_lower_right(L, (rank + 1) * L)
+        else:       # CPU (gloo tests of the host logic): the same mask, materialised
+            mask = torch.ones(L, (rank + 1) * L, dtype=torch.bool).tril(diagonal=rank * L)
+        o = nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask, enable_gqa=nh != nkv)
     return attn.o_proj(o.transpose(1, 2).reshape(b, L, nh * d))
 
 
