@@ -14,22 +14,25 @@
 //   O: Yo[m,p]   = sum_n C[m,n] S_c[n,p]          (S_c = state entering the chunk, bf16 copy in smem)
 //   S: dS[n,p]   = sum_k B[k,n] * (dt_k exp(cs_last - cs_k) x[k,p])      tcgen05 SS into a FRESH accumulator
 //      S_{c+1}   = exp(cs_last) * S_c + dS                               WG_S: the running state lives in REGISTERS
-//      y[m,p]    = Yd + exp(cs_m) * Yo + D * x[m,p]   [* silu(z)]         WG_C: TMEM -> regs -> bf16 tile staged in the
-//                                                                         dead x stage -> TMA tensor store
+//      y[m,p]    = Yd + exp(cs_m) * Yo + D * x[m,p]   [* silu(z)]         WG_C: TMEM -> regs -> bf16, each warp through
+//                                                                         its own staging area -> its own TMA stores
 // Decay, mask and cumsum stay in fp32 registers; only the four contractions touch the tensor cores.
 //
-// Round-2 dataflow (why it looks like this: profiles/r02_ssd_restructure.md).  The round-1 kernel kept the state in a
-// TMEM accumulator that the S MMA accumulated onto, so every chunk paid MMA -> commit -> TMEM load / decay / store ->
-// MMA as a serial chain, and one in-order issuing thread coupled that chain to the C.B^T -> M -> D chain.  Here
-//   * the S MMA never accumulates across chunks: the recurrence is 80 FMAs per thread in WG_S's registers, everything
-//     else is feed-forward;
-//   * C.B^T is double-buffered in TMEM and M overwrites it in place, so G(c+1) / M(c+1) run a chunk ahead;
-//   * two issuing threads: (G, D) and (S, O);  the TMA producer polls its three rings instead of waiting in order;
-//   * register budgets per role via setmaxnreg (WG_S holds the 128x80 fp32 state: 80 registers per thread).
+// Round-2 dataflow (why it looks like this: profiles/r02_ssd_restructure.md, profiles/r02_ssd_v5.md).  The round-1 kernel
+// kept the state in a TMEM accumulator that the S MMA accumulated onto, so every chunk paid MMA -> commit -> TMEM load /
+// decay / store -> MMA as a serial chain, and one in-order issuing thread coupled that chain to the C.B^T -> M -> D chain.
+//   * The S MMA never accumulates across chunks: the recurrence is 80 FMAs per thread in WG_S's registers, everything
+//     else is feed-forward.
+//   * C.B^T is double-buffered in TMEM and M overwrites it in place, so G / M run ahead of the state path; the M builders
+//     take cs / dt from L2 one chunk ahead (not from the x stage), so M(c) is ready when x(c) lands.
+//   * ONE MMA-issuing thread and one TMA thread, both POLLING (mbarrier.test_wait) their streams / rings instead of
+//     waiting in program order; a group of 8 MMAs is always issued back to back.
+//   * The x stage goes back to the TMA producer with the D commit: y is staged per epilogue warp in its own 3 KB.
+//   * Register budgets per role via setmaxnreg (WG_S holds the 128x80 fp32 state: 80 registers per thread).
 //
-// Warp roles (640 threads): warps 0-3 = WG_A (diagonal M blocks, block 2 of the last row quarter), warps 4-7 = WG_X
-// (x scaling for the S MMA + the off-diagonal M blocks 0/1), warps 8-11 = WG_S (state), warps 12-15 = WG_C (epilogue),
-// warp 16 = TMA producer, warp 17 = issuer of G / D + TMEM owner, warp 18 = issuer of S / O.
+// Warp roles (640 threads): warps 0-3 = WG_A (diagonal M blocks + one off-diagonal block), warps 4-7 = WG_X (x scaling
+// for the S MMA), warps 8-11 = WG_S (state), warps 12-15 = WG_C (epilogue), warp 16 = TMA producer, warp 17 = MMA issuer
+// + TMEM owner, warps 18 / 19 = M helpers (off-diagonal blocks 0 / 1 of row quarters 2 / 3).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "ssd.h"
@@ -44,11 +47,6 @@ using namespace sm100;
 
 namespace tc {
 constexpr int Q = 128, P = 80, N = 128;
-// L2 prefetch distance of the TMA producer (chunks ahead of the shared-memory loads; 0 = off).  x / cs / dt are prefetched
-// by every CTA, the B / C tiles (shared by the heads of a group) by the group's first head only.
-#ifndef TV_SSD_PF
-#define TV_SSD_PF 0
-#endif
 // Back-off of the two polling threads after a pass that found nothing to do (ns; 0 = spin).  Every probe is a shared-memory
 // operation, and the shared-memory pipe is what bounds this kernel.
 #ifndef TV_POLL_NS_PROD
@@ -58,7 +56,7 @@ constexpr int Q = 128, P = 80, N = 128;
 #define TV_POLL_NS_MMA 0
 #endif
 constexpr int THREADS = 640;
-constexpr int W_A = 0, W_X = 4, W_S = 8, W_C = 12, W_PROD = 16, W_MMA = 17;   // warps 18 / 19: M helpers   // first warp of each role
+constexpr int W_A = 0, W_X = 4, W_S = 8, W_C = 12, W_PROD = 16, W_MMA = 17;   // first warp of each role (18 / 19: M helpers)
 // Registers per thread after setmaxnreg.  The pool is what the CTA was LAUNCHED with (640 threads x 96 registers, the
 // most __launch_bounds__(640) allows), not the SM's register file: the five warpgroups must sum to 5 x 96 = 480.
 constexpr int REG_LAUNCH = 96;
@@ -223,7 +221,6 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBAR * 8);
-  volatile int* progress = reinterpret_cast<volatile int*>(smem + OFF_BAR + NBAR * 8 + 8);   // x tiles issued by the producer
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
   const int hpg = a.H / a.G;
@@ -243,7 +240,6 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
     }
     mbar_init(&bars[XSFULL], 4); mbar_init(&bars[STDONE], 1); mbar_init(&bars[DSFREE], 4); mbar_init(&bars[SFULL], 4);
     mbar_init(&bars[YOFULL], 1); mbar_init(&bars[YDFULL], 1); mbar_init(&bars[YDFREE], 4); mbar_init(&bars[YOFREE], 4);
-    *progress = 0;
     fence_mbar_init();
   }
   if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
@@ -286,7 +282,6 @@ ssd_fused_kernel(const __grid_constant__ tc::Maps maps, const tc::Args a) {
               bulk_load(xs_ + TILE_X, a.cs + (row0 + (int64_t)cx * a.H) * Q, 512, &bars[FULLX0 + s]);
               bulk_load(xs_ + TILE_X + 512, a.dt_act + (row0 + (int64_t)cx * a.H) * Q, 512, &bars[FULLX0 + s]);
               ++cx;
-              *progress = cx;
             }
           }
           if (cb < n) {
