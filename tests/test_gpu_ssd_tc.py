@@ -90,3 +90,18 @@ def test_reuse_dt_cumsum_refuses_a_workspace_filled_from_other_inputs(tv):
         tv.mamba_chunk_scan_combined(x, dt.clone(), A, B, C, 128, _reuse_dt_cumsum=True, **kw)
     with pytest.raises(ValueError, match="reuse_dt_cumsum"):                                         # other dims
         tv.mamba_chunk_scan_combined(x[:, :256], dt[:, :256], A, B[:, :256], C[:, :256], 128, _reuse_dt_cumsum=True, **kw)
+
+
+def test_chunk_size_256_runs_on_the_tensor_core_kernel(tv):
+    """The reference class default is chunk_size = 256 (configuration_nano.py:137-175): any multiple of 128 is served by the
+    tcgen05 kernel (which walks 128-token chunks internally -- the chunk size only moves rounding points)."""
+    assert tv.ssd_kernel_family(torch.bfloat16, 80, 128, 256) == "tcgen05"
+    b, L, H, G = 1, 1500, 8, 2
+    x, dt, A, B, C, D, z, dt_bias = _ssd_inputs(b, L, H, 80, G, 128, torch.bfloat16, seed=21)
+    init = torch.randn(b, H, 80, 128, device="cuda") * 0.5
+    for q in (256, 512):
+        out, fin = tv.mamba_chunk_scan_combined(x, dt, A, B, C, q, D=D, dt_bias=dt_bias, dt_softplus=True,
+                                                initial_states=init, return_final_states=True)
+        ref, ref_fin = R.ssd_chunked_ref(*_cpu(x, dt, A, B, C), q, D=D.cpu(), dt_bias=dt_bias.cpu(), dt_softplus=True,
+                                         initial_states=init.cpu())
+        assert relerr(out, ref) < TOL and relerr(fin, ref_fin) < TOL, q

@@ -996,7 +996,10 @@ static std::mutex g_dt_tags_mu;
 static std::unordered_map<const void*, DtTag> g_dt_tags;
 
 bool tc_supported(const tv_ssd_params& p) {
-  if (p.dtype != TV_BF16 || p.headdim != tc::P || p.dstate != tc::N || p.chunk_size != tc::Q) return false;
+  // chunk_size: any multiple of 128 (the reference class default is 256, configuration_nano.py:137-175).  The chunk size only
+  // sets where the recurrence is re-anchored -- the result is the same function of the inputs, up to rounding -- so the kernel
+  // always walks chunks of 128 tokens.
+  if (p.dtype != TV_BF16 || p.headdim != tc::P || p.dstate != tc::N || p.chunk_size <= 0 || p.chunk_size % tc::Q != 0) return false;
   if (p.nheads % p.ngroups != 0) return false;
   auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
   if (!al16(p.x) || !al16(p.B) || (p.mode == TV_SSD_FULL && (!al16(p.C) || ((uintptr_t)p.out & 31) != 0))) return false;
@@ -1010,16 +1013,18 @@ bool tc_supported(const tv_ssd_params& p) {
 }
 
 size_t tc_workspace_bytes(const tv_ssd_params& p) {
-  const int64_t nchunks = ceil_div(p.seqlen, p.chunk_size);
-  const size_t per = (size_t)p.batch * nchunks * p.nheads * p.chunk_size * sizeof(float);
+  const int64_t nchunks = ceil_div(p.seqlen, tc::Q);
+  const size_t per = (size_t)p.batch * nchunks * p.nheads * tc::Q * sizeof(float);
   // dt | cumsum | first_chunk | partial shard summaries.  The size does not depend on `mode`: the sharded path calls
   // DT_ONLY, STATE_ONLY and FULL on ONE workspace (reuse_dt_cumsum), which must not be re-allocated in between.
   return 2 * ((per + 255) & ~(size_t)255) + ((((size_t)p.batch * p.nheads * sizeof(int)) + 255) & ~(size_t)255) +
          (size_t)p.batch * p.nheads * kMaxStateSplit * tc::P * tc::N * sizeof(float);
 }
 
-int ssd_tc_forward(const tv_ssd_params& p, void* workspace, cudaStream_t s) {
+int ssd_tc_forward(const tv_ssd_params& p_in, void* workspace, cudaStream_t s) {
   using namespace tc;
+  tv_ssd_params p = p_in;
+  p.chunk_size = Q;                              // internal chunks of 128 tokens, whatever multiple the caller asked for
   const int nchunks = (int)ceil_div(p.seqlen, Q);
   const size_t per = (((size_t)p.batch * nchunks * p.nheads * Q * sizeof(float)) + 255) & ~(size_t)255;
   float* dt_act = (float*)workspace;
