@@ -491,8 +491,8 @@ def run_hybrid(args):
                                reference's default schedule (evaluate.py:167-172)                          (configs[4])
     N > 1: N / S replicas of ONE sample each, every sample sharded over S = --shard GPUs (default 1: N independent replicas,
     no collective on the data path).  With S > 1 the layer loop runs sequence-sharded (Mamba-2 layers: conv halo + boundary
-    states; attention layers: K/V all-gather; hybrid9b only -- a pyramid-drop changes the shard lengths), so BASELINE
-    configs[4]'s "batch 4 across 8 GPUs" is `--gpus 8 --shard 2` without the drop, or 8 x batch 1 with it."""
+    states; attention layers: K/V all-gather; after a pyramid-drop the survivors are re-balanced with one all-to-all), so
+    BASELINE configs[4]'s "batch 4 across 8 GPUs" is `--workload hybrid9b-pdrop --gpus 8 --shard 2`."""
     import timeviper_b200 as tv
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -502,8 +502,8 @@ def run_hybrid(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     drop = args.workload == "hybrid9b-pdrop"
     S = max(1, args.shard)
-    if world % S or (S > 1 and drop):
-        raise SystemExit("bench.py: --shard must divide the number of GPUs and is not combined with the pyramid-drop workload")
+    if world % S:
+        raise SystemExit("bench.py: --shard must divide the number of GPUs")
     grp = None
     if S > 1:       # process groups of S consecutive ranks; every rank creates all of them (collective call)
         for g0 in range(0, world, S):
@@ -516,7 +516,9 @@ def run_hybrid(args):
     torch.manual_seed(rank // S)                  # the ranks of one sample hold the same weights
     with torch.device("cuda"):
         model = tv.HybridCausalLM(cfg).to(torch.bfloat16).eval()
-    x = torch.randn(1, L // S, cfg.hidden_size, device="cuda").to(torch.bfloat16)     # this rank's shard of its sample
+    from timeviper_b200.hybrid import shard_bounds
+    so = shard_bounds(L, S)
+    x = torch.randn(1, so[rank % S + 1] - so[rank % S], cfg.hidden_size, device="cuda").to(torch.bfloat16)   # this rank's shard
     pd = dict(pdrop_type="uni_14_0.8-attn_21_0.6-attn_30_0.4-attn_39_0.2", first_vision_token_position=0,
               num_vision_tokens=L - text, text_prompt_len=text) if drop else None
     run = lambda inp: model(inputs_embeds=inp, pdrop=pd, group=grp)

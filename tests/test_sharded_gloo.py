@@ -161,3 +161,57 @@ def test_sharded_hybrid_stack_equals_unsharded_gloo(world, L):
         assert r["err"] < 1e-6, r
         if r["rank"] == world - 1:
             assert r["logit_err"] < 1e-6, r
+
+
+def _pdrop_worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import timeviper_b200 as tv
+        from timeviper_b200.hybrid import shard_bounds
+        torch.manual_seed(23)
+        pattern, pre, V, post = "M*-M*", 3, 100, 10
+        cfg = tv.Mamba2Config(hidden_size=32, mamba_num_heads=4, mamba_head_dim=8, n_groups=2, ssm_state_size=16,
+                              chunk_size=32, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                              num_attention_heads=4, num_key_value_heads=2, head_dim=8, intermediate_size_mlp=48, vocab_size=50)
+        model = tv.HybridPrefillStack(cfg).double()
+        with torch.no_grad():
+            for layer in model.layers:
+                if layer.block_type == "mamba":
+                    layer.mixer.A_log.copy_(torch.log(torch.rand(4) * 3 + 0.05))
+                    layer.mixer.dt_bias.copy_(torch.randn(4) * 0.5 - 2.0)
+                    layer.mixer.D.copy_(torch.randn(4))
+        L = pre + V + post
+        x = torch.randn(1, L, 32, dtype=torch.float64)
+        pd = dict(pdrop_type="uni_2_0.8-attn_4_0.5", first_vision_token_position=pre, num_vision_tokens=V, text_prompt_len=pre + post)
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        ref = R.hybrid_forward_ref(sd, x, pattern=pattern, num_heads=4, head_dim=8, n_groups=2, ssm_state_size=16,
+                                   chunk_size=32, attn_heads=4, kv_heads=2, attn_head_dim=8, dtype=torch.float64, pdrop=pd)
+        offs = shard_bounds(L, world)
+        with torch.no_grad():
+            h = model(inputs_embeds=x[:, offs[rank]:offs[rank + 1]], group=dist.group.WORLD, mixer_ops=_oracle_ops(), pdrop=pd)
+        new = shard_bounds(ref.shape[1], world)
+        mine = ref[:, new[rank]:new[rank + 1]]
+        out_q.put({"rank": rank, "shape_ok": tuple(h.shape) == tuple(mine.shape),
+                   "err": float((h - mine).abs().max() / ref.abs().max()) if tuple(h.shape) == tuple(mine.shape) else 1.0})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pyramid_drop_equals_unsharded_gloo(world):
+    """TransV / pyramid-drop over a sequence-sharded sample (uniform stage, then an attention-ranked stage with the
+    distributed softmax and the all-to-all re-balancing; unequal shards) against the unsharded oracle stack, fp64, gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pdrop_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in results:
+        assert r["shape_ok"] and r["err"] < 1e-6, r

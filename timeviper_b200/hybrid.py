@@ -84,31 +84,57 @@ def _two_part_attention(q, k, v, L, rep):
         return None
 
 
-def sharded_attention_forward(attn, hidden_states, group=None):
-    """Causal attention of a sequence-sharded layer: rank r holds tokens [r*Ls, (r+1)*Ls) (equal shards).  K and V of every
-    rank are all-gathered (GQA: 2 x kv_heads x head_dim values per token, 4 KB at the 9B shape -- 1/10 of the hidden state),
-    each rank attends its queries over the keys of ranks <= r with a LOWER-RIGHT aligned causal mask (its queries are the
-    last Ls positions of that key range), which library SDPA takes without materialising a mask.  The work per rank grows
-    with r (causal); a zig-zag split would balance it but breaks the contiguous shards the Mamba-2 layers need."""
+def shard_bounds(total, world):
+    """Balanced contiguous split of `total` tokens over `world` ranks: offsets [0, ..., total] (first ranks one longer)."""
+    base, rem = divmod(total, world)
+    offs = [0]
+    for r in range(world):
+        offs.append(offs[-1] + base + (1 if r < rem else 0))
+    return offs
+
+
+def _gather_lengths(L, device, group):
+    """Shard lengths of every rank (host ints; one small all-gather + sync, once per forward or per drop)."""
+    world = dist.get_world_size(group)
+    t = torch.tensor([L], dtype=torch.int64, device=device)
+    out = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return [int(v) for v in out.tolist()]
+
+
+def sharded_attention_forward(attn, hidden_states, group=None, lens=None):
+    """Causal attention of a sequence-sharded layer: rank r holds a contiguous shard (lengths `lens`, default: all equal to
+    this rank's).  K and V of every rank are all-gathered (GQA: 2 x kv_heads x head_dim values per token, 4 KB at the 9B
+    shape -- 1/10 of the hidden state), each rank attends its queries over the keys of ranks <= r with a LOWER-RIGHT
+    aligned causal mask (its queries are the last positions of that key range).  The work per rank grows with r (causal);
+    a zig-zag split would balance it but breaks the contiguous shards the Mamba-2 layers need."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     b, L, _ = hidden_states.shape
+    if lens is None:
+        lens = [L] * world
+    Lmax = max(lens)
     nh, nkv, d = attn.num_heads, attn.num_key_value_heads, attn.head_dim
     q = attn.q_proj(hidden_states).view(b, L, nh, d).transpose(1, 2)
-    kv = torch.stack([attn.k_proj(hidden_states), attn.v_proj(hidden_states)]).contiguous()        # (2, b, L, nkv*d)
+    kv = torch.stack([attn.k_proj(hidden_states), attn.v_proj(hidden_states)])                       # (2, b, L, nkv*d)
+    if L < Lmax:
+        kv = nn.functional.pad(kv, (0, 0, 0, Lmax - L))
+    kv = kv.contiguous()
     gathered = torch.empty((world,) + tuple(kv.shape), dtype=kv.dtype, device=kv.device)
     dist.all_gather_into_tensor(gathered.view(-1), kv.view(-1), group=group)
-    gathered = gathered[:rank + 1]                                                                   # keys this rank may see
-    k = gathered[:, 0].permute(1, 0, 2, 3).reshape(b, (rank + 1) * L, nkv, d).transpose(1, 2)
-    v = gathered[:, 1].permute(1, 0, 2, 3).reshape(b, (rank + 1) * L, nkv, d).transpose(1, 2)
+    parts = [gathered[j, :, :, :lens[j]] for j in range(rank + 1)]                                    # keys this rank may see
+    kv_all = parts[0] if rank == 0 else torch.cat(parts, dim=2)                                       # (2, b, Lk, nkv*d)
+    Lk = kv_all.shape[2]
+    k = kv_all[0].view(b, Lk, nkv, d).transpose(1, 2)
+    v = kv_all[1].view(b, Lk, nkv, d).transpose(1, 2)
     o = None
     if hidden_states.is_cuda and rank > 0 and q.dtype in (torch.bfloat16, torch.float16):   # the cuDNN op is half-precision only
         o = _two_part_attention(q, k, v, L, nh // nkv)
     if o is None:
         if hidden_states.is_cuda:
             from torch.nn.attention.bias import causal_lower_right
-            mask = causal_lower_right(L, (rank + 1) * L)
+            mask = causal_lower_right(L, Lk)
         else:       # CPU (gloo tests of the host logic): the same mask, materialised
-            mask = torch.ones(L, (rank + 1) * L, dtype=torch.bool).tril(diagonal=rank * L)
+            mask = torch.ones(L, Lk, dtype=torch.bool).tril(diagonal=Lk - L)
         o = nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask, enable_gqa=nh != nkv)
     return attn.o_proj(o.transpose(1, 2).reshape(b, L, nh * d))
 
@@ -136,8 +162,9 @@ class HybridBlock(nn.Module):
         self.norm = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
         self.mixer = {"mamba": Mamba2MixerPrefill, "attention": Attention, "mlp": MLP}[self.block_type](config, layer_idx)
 
-    def forward(self, hidden_states, cache_params=None, cache_position=None, group=None, mixer_ops=None):
-        """group: the sequence is sharded contiguously over this process group (equal shards, rank order = token order)."""
+    def forward(self, hidden_states, cache_params=None, cache_position=None, group=None, mixer_ops=None, lens=None):
+        """group: the sequence is sharded contiguously over this process group (rank order = token order; `lens`: the shard
+        lengths when they are not all equal)."""
         residual = hidden_states.to(torch.float32) if self.residual_in_fp32 else hidden_states
         h = self.norm(hidden_states.to(self.norm.weight.dtype))
         sharded = group is not None and dist.get_world_size(group) > 1
@@ -149,7 +176,7 @@ class HybridBlock(nn.Module):
             else:
                 h = self.mixer(h, cache_params=cache_params, cache_position=cache_position)
         elif self.block_type == "attention" and sharded:
-            h = sharded_attention_forward(self.mixer, h, group)
+            h = sharded_attention_forward(self.mixer, h, group, lens)
         else:
             h = self.mixer(h)
         return residual + h
@@ -194,6 +221,66 @@ def pdrop_select(h, stage, kind, ratios, attn, vision_index, num_vision_tokens, 
     return (top + vision_index).sort().values, vision_index + image_tokens
 
 
+@torch.no_grad()
+def sharded_pdrop(h, offs, group, stage, kind, ratios, attn, vision_index, num_vision_tokens, text_prompt_len):
+    """``pdrop_select`` + the token drop for ONE sample whose sequence is sharded over `group` (this rank holds the global
+    positions offs[rank] .. offs[rank+1]).  Returns this rank's shard of the shortened sequence, re-balanced
+    (``shard_bounds``), and the new offsets.  Same rule as the unsharded path: 'uni' needs no communication; 'attn' broadcasts
+    the query row of the last prompt token, every rank scores its own keys, the softmax is normalised with the global
+    maximum / sum (two small all-reduces), and the per-token weights of the vision block (4 bytes per token) are gathered so
+    that every rank takes the same top-k.  The surviving tokens then move with ONE all-to-all."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev, dtype = h.device, h.dtype
+    image_tokens = int(num_vision_tokens * ratios[stage])
+    keep = int(num_vision_tokens * ratios[stage + 1])
+    lo, hi = offs[rank], offs[rank + 1]
+    total = offs[-1]
+    if "attn" in kind:
+        if attn is None:
+            raise ValueError("an attention-ranked drop must sit on an attention layer (modeling_nano.py:1824)")
+        pq = text_prompt_len + image_tokens - 1                                # global position of the last prompt token
+        owner = max(r for r in range(world) if offs[r] <= pq)
+        nh, nkv, d = attn.num_heads, attn.num_key_value_heads, attn.head_dim
+        q = attn.q_proj(h[0, pq - lo:pq - lo + 1]).view(nh, 1, d) if rank == owner else torch.empty(nh, 1, d, dtype=dtype, device=dev)
+        dist.broadcast(q, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        n_loc = max(0, min(hi, pq + 1) - lo)                                   # my keys the causal row can see
+        k = attn.k_proj(h[0, :n_loc]).view(n_loc, nkv, d).transpose(0, 1).repeat_interleave(nh // nkv, dim=0)
+        sc = ((q @ k.transpose(1, 2)) / (d ** 0.5))[:, 0].float()              # (nh, n_loc), scores rounded to dtype first
+        m = sc.max(dim=-1).values if n_loc > 0 else torch.full((nh,), float("-inf"), device=dev)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        e = torch.exp(sc - m[:, None])
+        z = e.sum(-1)
+        dist.all_reduce(z, op=dist.ReduceOp.SUM, group=group)
+        w = (e / z[:, None]).to(dtype).mean(0)                                 # (n_loc,): mean over heads, in dtype
+        # my part of the vision block [vision_index, vision_index + image_tokens)
+        a, b_ = max(lo, vision_index), min(hi, vision_index + image_tokens, pq + 1)
+        mine = w[a - lo:b_ - lo] if b_ > a else w[:0]
+        cnt = [max(0, min(offs[r + 1], vision_index + image_tokens) - max(offs[r], vision_index)) for r in range(world)]
+        pad = torch.zeros(max(cnt), dtype=dtype, device=dev)
+        pad[:mine.numel()] = mine
+        allw = torch.empty(world, max(cnt), dtype=dtype, device=dev)
+        dist.all_gather_into_tensor(allw.view(-1), pad, group=group)
+        wfull = torch.cat([allw[r, :cnt[r]] for r in range(world)])            # (image_tokens,), identical on every rank
+        top = wfull.topk(keep).indices.cpu()
+    elif "uni" in kind:
+        top = torch.linspace(0, image_tokens - 1, keep, dtype=torch.long)
+    else:
+        raise NotImplementedError(kind)
+    start = vision_index + image_tokens
+    kept = torch.cat([torch.arange(0, vision_index), (top + vision_index).sort().values, torch.arange(start, total)])   # host
+    new_offs = shard_bounds(kept.numel(), world)
+    # kept is sorted: the tokens of old shard s are the new positions [pos[s], pos[s+1])
+    pos = torch.searchsorted(kept, torch.tensor(offs)).tolist()
+    a, b_ = pos[rank], pos[rank + 1]
+    send = h[:, (kept[a:b_] - lo).to(dev)].contiguous()[0]                     # (b_-a, hidden)
+    ovl = lambda x0, x1, y0, y1: max(0, min(x1, y1) - max(x0, y0))
+    in_splits = [ovl(a, b_, new_offs[r], new_offs[r + 1]) for r in range(world)]
+    out_splits = [ovl(pos[s_], pos[s_ + 1], new_offs[rank], new_offs[rank + 1]) for s_ in range(world)]
+    out = torch.empty(sum(out_splits), h.shape[-1], dtype=dtype, device=dev)
+    dist.all_to_all_single(out, send, out_splits, in_splits, group=group)
+    return out.unsqueeze(0), new_offs
+
+
 class HybridPrefillStack(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -214,8 +301,8 @@ class HybridPrefillStack(nn.Module):
         ``group`` (a torch.distributed process group of more than one rank): the inputs are this rank's contiguous shard of
         ONE sequence (equal shards, rank order = token order) and so is the result; Mamba-2 layers run
         ``sharded_mixer_forward`` (conv halo + boundary-state exchange), attention layers all-gather K / V
-        (``sharded_attention_forward``), everything else is token-local.  Not combined with ``pdrop`` (a drop changes the
-        shard lengths and would need a re-balancing step).
+        (``sharded_attention_forward``), everything else is token-local.  With ``pdrop`` the positions in it are GLOBAL
+        (whole-sequence) positions; after every drop the survivors are re-balanced over the ranks (``sharded_pdrop``).
         ``cache_params`` (reference cache interface) receives the conv / SSM states of every Mamba-2 layer.
         Limits (stated, not hidden): no ``attention_mask`` (batch 1 or unpadded batches only) and the attention layers do
         not write a KV cache, so this stack prefills and scores the last position; token-by-token decode after it needs
@@ -225,21 +312,32 @@ class HybridPrefillStack(nn.Module):
         h = self.embeddings(input_ids) if inputs_embeds is None else inputs_embeds
         pos = torch.arange(h.shape[1])          # on the HOST: the mixer branches on cache_position[0] > 0 (no device sync)
         sharded = group is not None and dist.get_world_size(group) > 1
+        lens = offs = None
         if pdrop is not None:
-            if sharded:
-                raise NotImplementedError("pyramid-drop over a sequence-sharded stack is not built")
             if h.shape[0] != 1:
                 raise NotImplementedError("pyramid-drop is wired for batch 1 (the reference's inference path)")
             kinds, drop_layers, ratios = parse_pdrop_type(pdrop["pdrop_type"])
+        if sharded and pdrop is not None:
+            lens = _gather_lengths(h.shape[1], h.device, group)
+            offs = [0]
+            for n_ in lens:
+                offs.append(offs[-1] + n_)
         for i, layer in enumerate(self.layers):
             if pdrop is not None and i in drop_layers:
                 st = drop_layers.index(i)
                 vi = pdrop["first_vision_token_position"]
-                top, start = pdrop_select(h[0], st, kinds[st], ratios, layer.mixer if layer.block_type == "attention" else None,
-                                          vi, pdrop["num_vision_tokens"], pdrop["text_prompt_len"])
-                h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)                 # :1981-1988
+                att = layer.mixer if layer.block_type == "attention" else None
+                if sharded:
+                    h, offs = sharded_pdrop(h, offs, group, st, kinds[st], ratios, att, vi, pdrop["num_vision_tokens"],
+                                            pdrop["text_prompt_len"])
+                    lens = [offs[r + 1] - offs[r] for r in range(len(offs) - 1)]
+                else:
+                    top, start = pdrop_select(h[0], st, kinds[st], ratios, att, vi, pdrop["num_vision_tokens"],
+                                              pdrop["text_prompt_len"])
+                    h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)             # :1981-1988
                 pos = torch.arange(h.shape[1])
-            h = layer(h, cache_params=cache_params, cache_position=pos, group=group if sharded else None, mixer_ops=mixer_ops)
+            h = layer(h, cache_params=cache_params, cache_position=pos, group=group if sharded else None, mixer_ops=mixer_ops,
+                      lens=lens)
         return self.norm_f(h)
 
 
