@@ -222,7 +222,7 @@ def pdrop_select(h, stage, kind, ratios, attn, vision_index, num_vision_tokens, 
 
 
 @torch.no_grad()
-def sharded_pdrop(h, offs, group, stage, kind, ratios, attn, vision_index, num_vision_tokens, text_prompt_len):
+def sharded_pdrop(h, offs, group, stage, kind, ratios, attn, vision_index, num_vision_tokens, text_prompt_len, trace=None):
     """``pdrop_select`` + the token drop for ONE sample whose sequence is sharded over `group` (this rank holds the global
     positions offs[rank] .. offs[rank+1]).  Returns this rank's shard of the shortened sequence, re-balanced
     (``shard_bounds``), and the new offsets.  Same rule as the unsharded path: 'uni' needs no communication; 'attn' broadcasts
@@ -268,6 +268,8 @@ def sharded_pdrop(h, offs, group, stage, kind, ratios, attn, vision_index, num_v
         raise NotImplementedError(kind)
     start = vision_index + image_tokens
     kept = torch.cat([torch.arange(0, vision_index), (top + vision_index).sort().values, torch.arange(start, total)])   # host
+    if trace is not None:
+        trace.append((top + vision_index).sort().values.clone())
     new_offs = shard_bounds(kept.numel(), world)
     # kept is sorted: the tokens of old shard s are the new positions [pos[s], pos[s+1])
     pos = torch.searchsorted(kept, torch.tensor(offs)).tolist()
@@ -329,12 +331,14 @@ class HybridPrefillStack(nn.Module):
                 att = layer.mixer if layer.block_type == "attention" else None
                 if sharded:
                     h, offs = sharded_pdrop(h, offs, group, st, kinds[st], ratios, att, vi, pdrop["num_vision_tokens"],
-                                            pdrop["text_prompt_len"])
+                                            pdrop["text_prompt_len"], trace=pdrop.get("_trace"))
                     lens = [offs[r + 1] - offs[r] for r in range(len(offs) - 1)]
                 else:
                     top, start = pdrop_select(h[0], st, kinds[st], ratios, att, vi, pdrop["num_vision_tokens"],
                                               pdrop["text_prompt_len"])
                     h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)             # :1981-1988
+                    if pdrop.get("_trace") is not None:     # tests: the surviving vision positions of this stage
+                        pdrop["_trace"].append(top.cpu().clone())
                 pos = torch.arange(h.shape[1])
             h = layer(h, cache_params=cache_params, cache_position=pos, group=group if sharded else None, mixer_ops=mixer_ops,
                       lens=lens)
