@@ -164,7 +164,7 @@ def main_causal_lm():
     print("causal_lm logits", tuple(out.logits.shape), out.logits.dtype, "->", os.path.getsize(path) // 1024, "KiB")
 
 
-def main_pdrop():
+def main_pdrop(merge_module="no_merge"):
     """TransV / pyramid-drop between layers: NemotronHModel.forward with ``use_pdrop`` (the hooks at
     modeling_nano.py:1634-1689 -> flash_rank_drop :2156 -> pdrop_no_pack :1779-2095), inference, batch 1, ``no_merge`` (the
     default of evaluate.py:167-177): a uniform drop before one layer and attention-ranked drops (query = last prompt token,
@@ -181,7 +181,7 @@ def main_pdrop():
     cfg = Cfg(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, mamba_n_groups=G, ssm_state_size=N,
               mamba_chunk_size=Q, mamba_d_conv=4, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
               layer_norm_epsilon=1e-5, num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd,
-              intermediate_size=mlp, vocab_size=100, use_pdrop=True, pdrop_type=pdrop_type, merge_module="no_merge")
+              intermediate_size=mlp, vocab_size=100, use_pdrop=True, pdrop_type=pdrop_type, merge_module=merge_module)
     cfg._attn_implementation = "eager"
     model = mn.NemotronHModel(cfg).float().eval()
     for k, v in model.pdrop_args.items():          # what NemotronHForCausalLM.set_pdrop_args does (:2459-2462)
@@ -198,6 +198,8 @@ def main_pdrop():
                 layer.mixer.dt_bias.copy_(torch.randn(H) * 0.5 - 2.0)
                 layer.mixer.D.copy_(torch.randn(H))
             layer.norm.weight.copy_(1.0 + 0.1 * torch.randn(hidden))
+        if merge_module == "CrossAttention":       # TransV: alpha is zero at init (no merge); a trained gate is not
+            model.alpha.copy_(torch.tensor([0.7, -0.5, 0.9]))
         x = torch.randn(1, pre + V + post, hidden)
         args = dict(is_interleaved=False, first_vision_token_positions=[torch.tensor(pre)], num_vision_tokens=[V],
                     text_prompt_lens=[pre + post])
@@ -206,8 +208,8 @@ def main_pdrop():
     blob = {k: v.detach().numpy() for k, v in model.state_dict().items()}
     blob.update(inputs_embeds=x.numpy(), last_hidden_state=hs.numpy(),
                 dims=np.array([hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pre, V, post], dtype=np.int64),
-                pattern=np.array(pattern), pdrop_type=np.array(pdrop_type))
-    path = os.path.join(out_dir, "pdrop_uni_attn_attn.npz")
+                pattern=np.array(pattern), pdrop_type=np.array(pdrop_type), merge_module=np.array(merge_module))
+    path = os.path.join(out_dir, "pdrop_uni_attn_attn.npz" if merge_module == "no_merge" else "transv_merge_uni_attn_attn.npz")
     np.savez_compressed(path, **blob)
     print("pdrop", tuple(x.shape), "->", tuple(hs.shape), os.path.getsize(path) // 1024, "KiB")
 
@@ -251,6 +253,7 @@ if __name__ == "__main__":
         main_causal_lm()
     elif "--pdrop-only" in sys.argv:
         main_pdrop()
+        main_pdrop("CrossAttention")
     else:
         main()
         main_hybrid()

@@ -365,7 +365,22 @@ def hybrid_forward_ref(p: dict, inputs_embeds: torch.Tensor, *, pattern: str, nu
                                           None if wk is None else wk.to(dtype), attn_heads, kv_heads, attn_head_dim,
                                           pdrop["first_vision_token_position"], pdrop["num_vision_tokens"], pdrop["text_prompt_len"])
             vi = pdrop["first_vision_token_position"]
-            h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)                            # :1981-1988
+            text = h[:, start:]
+            if pdrop.get("merge_module", "no_merge") == "CrossAttention":                          # TransV, :1748-1777
+                keep_mask = torch.ones(start - vi, dtype=torch.bool)
+                keep_mask[top - vi] = False
+                dropped = h[:, vi:start][:, keep_mask]                                             # the tokens about to go
+                mp_ = f"merge_modules.{st}."
+                q = F.linear(text, p[mp_ + "q_proj.weight"].to(dtype)).view(1, -1, attn_heads, attn_head_dim).transpose(1, 2)
+                k = F.linear(dropped, p[mp_ + "k_proj.weight"].to(dtype)).view(1, -1, kv_heads, attn_head_dim).transpose(1, 2)
+                v = F.linear(dropped, p[mp_ + "v_proj.weight"].to(dtype)).view(1, -1, kv_heads, attn_head_dim).transpose(1, 2)
+                k = k.repeat_interleave(attn_heads // kv_heads, dim=1)
+                v = v.repeat_interleave(attn_heads // kv_heads, dim=1)
+                att = ((q @ k.transpose(-1, -2)) / math.sqrt(attn_head_dim)).softmax(-1)          # cross attention, no mask
+                merged = F.linear((att @ v).transpose(1, 2).reshape(1, text.shape[1], attn_heads * attn_head_dim),
+                                  p[mp_ + "o_proj.weight"].to(dtype))
+                text = text + torch.tanh(p["alpha"][st].to(dtype)) * merged                       # :1766-1768
+            h = torch.cat([h[:, :vi], h[:, top], text], dim=1)                                    # :1981-1988
             L = h.shape[1]
         x = rmsnorm_ref(h, p[pre + "norm.weight"], eps, dtype)                                    # :941
         sub = {k[len(pre) + 6:]: v for k, v in p.items() if k.startswith(pre + "mixer.")}

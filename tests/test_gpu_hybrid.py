@@ -86,7 +86,7 @@ def test_pyramid_drop_against_reference_golden(dtype, tol):
                           num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd, intermediate_size_mlp=mlp,
                           vocab_size=100)
     model = tv.HybridPrefillStack(cfg)
-    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type")
+    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type", "merge_module")
     model.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files if k not in skip}, strict=True)
     model = model.to(dtype).cuda().eval()
     x = torch.from_numpy(z["inputs_embeds"]).to(dtype).cuda()
@@ -101,3 +101,24 @@ def test_pyramid_drop_against_reference_golden(dtype, tol):
         # both runs kept (text and prefix rows are always kept) -- and most vision rows must agree
         close = ((out.float().cpu() - ref).abs().amax(-1) / ref.abs().max()) < tol
         assert bool(close[0, :pre].all()) and bool(close[0, -post:].all()) and float(close.float().mean()) > 0.8
+
+
+def test_transv_merge_module_against_reference_golden():
+    """TransV with its cross-attention merge module (reference parameter names ``merge_modules.N.*`` and ``alpha``), fp32,
+    against the reference's own forward."""
+    import timeviper_b200 as tv
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "transv_merge_uni_attn_attn.npz"))
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pre, V, post = [int(v) for v in z["dims"]]
+    pattern, ptype = str(z["pattern"]), str(z["pdrop_type"])
+    cfg = tv.Mamba2Config(hidden_size=hidden, mamba_num_heads=H, mamba_head_dim=P, n_groups=G, ssm_state_size=N,
+                          chunk_size=Q, num_hidden_layers=len(pattern), hybrid_override_pattern=pattern,
+                          num_attention_heads=ah, num_key_value_heads=kvh, head_dim=ahd, intermediate_size_mlp=mlp,
+                          vocab_size=100, merge_module="CrossAttention", pdrop_type=ptype)
+    model = tv.HybridPrefillStack(cfg)
+    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type", "merge_module")
+    model.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files if k not in skip}, strict=True)
+    model = model.cuda().eval()
+    pd = dict(pdrop_type=ptype, first_vision_token_position=pre, num_vision_tokens=V, text_prompt_len=pre + post)
+    out = model(inputs_embeds=torch.from_numpy(z["inputs_embeds"]).cuda(), pdrop=pd)
+    ref = torch.from_numpy(z["last_hidden_state"])
+    assert out.shape == ref.shape and relerr(out, ref) < 1e-4

@@ -188,7 +188,7 @@ def test_pdrop_oracle_matches_reference_golden():
     import os
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pdrop_uni_attn_attn.npz"))
     hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pre, V, post = [int(v) for v in z["dims"]]
-    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type")
+    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type", "merge_module")
     sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in skip}
     out = R.hybrid_forward_ref(sd, torch.from_numpy(z["inputs_embeds"]), pattern=str(z["pattern"]), num_heads=H, head_dim=P,
                                n_groups=G, ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd,
@@ -197,3 +197,21 @@ def test_pdrop_oracle_matches_reference_golden():
     ref = torch.from_numpy(z["last_hidden_state"])
     assert out.shape == ref.shape == (1, pre + int(V * 0.25) + post, hidden)
     assert float((out - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+def test_transv_merge_oracle_matches_reference_golden():
+    """TransV: pyramid-drop WITH the cross-attention merge module (the dropped vision tokens are read by the text tokens
+    through a gated cross attention before they go), through the reference's own NemotronHModel.forward."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "transv_merge_uni_attn_attn.npz"))
+    hidden, H, P, G, N, Q, ah, kvh, ahd, mlp, pre, V, post = [int(v) for v in z["dims"]]
+    skip = ("pattern", "dims", "inputs_embeds", "last_hidden_state", "pdrop_type", "merge_module")
+    sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in skip}
+    out = R.hybrid_forward_ref(sd, torch.from_numpy(z["inputs_embeds"]), pattern=str(z["pattern"]), num_heads=H, head_dim=P,
+                               n_groups=G, ssm_state_size=N, chunk_size=Q, attn_heads=ah, kv_heads=kvh, attn_head_dim=ahd,
+                               pdrop=dict(pdrop_type=str(z["pdrop_type"]), first_vision_token_position=pre,
+                                          num_vision_tokens=V, text_prompt_len=pre + post, merge_module="CrossAttention"))
+    ref = torch.from_numpy(z["last_hidden_state"])
+    assert out.shape == ref.shape and float((out - ref).abs().max() / ref.abs().max()) < 2e-5
+    nomerge = np.load(os.path.join(os.path.dirname(__file__), "golden", "pdrop_uni_attn_attn.npz"))["last_hidden_state"]
+    assert float(np.abs(nomerge - z["last_hidden_state"]).max()) > 1e-2      # the merge really changes the result

@@ -34,6 +34,9 @@ class Mamba2Config:
     mlp_hidden_act: str = "relu2"
     residual_in_fp32: bool = False
     vocab_size: int = 131072
+    # TransV (configuration_nano.py:177-179): cross-attention merge of the dropped vision tokens into the text tokens
+    merge_module: str = "no_merge"
+    pdrop_type: str = None
 
     @property
     def intermediate_size(self):

@@ -53,6 +53,20 @@ class Attention(nn.Module):
         return self.o_proj(o.transpose(1, 2).reshape(b, L, self.num_heads * self.head_dim))
 
 
+def cross_attention(attn, hidden_states, encoder_hidden_states):
+    """TransV merge module (``Qwen2VLSdpaCrossAttention.forward``, merge_modules/cross_attention.py:225-324, built on the
+    NemotronH attention dims): the text tokens (queries) read the vision tokens that a pyramid-drop stage is about to discard
+    (keys / values); no mask, no rotary embedding, library SDPA."""
+    b, Lq, _ = hidden_states.shape
+    Lk = encoder_hidden_states.shape[1]
+    nh, nkv, d = attn.num_heads, attn.num_key_value_heads, attn.head_dim
+    q = attn.q_proj(hidden_states).view(b, Lq, nh, d).transpose(1, 2)
+    k = attn.k_proj(encoder_hidden_states).view(b, Lk, nkv, d).transpose(1, 2)
+    v = attn.v_proj(encoder_hidden_states).view(b, Lk, nkv, d).transpose(1, 2)
+    o = nn.functional.scaled_dot_product_attention(q, k, v, is_causal=False, enable_gqa=nh != nkv)
+    return attn.o_proj(o.transpose(1, 2).reshape(b, Lq, nh * d))
+
+
 _two_part_ok = True
 
 
@@ -292,6 +306,18 @@ class HybridPrefillStack(nn.Module):
         self.embeddings = nn.Embedding(config.vocab_size, config.hidden_size)
         self.layers = nn.ModuleList([HybridBlock(config, i) for i in range(config.num_hidden_layers)])
         self.norm_f = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
+        # TransV merge modules (modeling_nano.py:1481-1523): one cross-attention per pyramid-drop stage + the gates alpha
+        self.merge_modules, self.alpha = None, None
+        if getattr(config, "merge_module", "no_merge") == "CrossAttention":
+            if not getattr(config, "pdrop_type", None):
+                raise ValueError("merge_module='CrossAttention' needs config.pdrop_type (one module per drop stage)")
+            kinds, drop_layers, _ = parse_pdrop_type(config.pdrop_type)
+            if any("drop" in k for k in kinds):
+                raise NotImplementedError("stages of the '...drop' kind (no merge at that stage) are not wired")
+            self.merge_modules = nn.ModuleList([Attention(config, layer_idx=i) for i in drop_layers])
+            self.alpha = nn.Parameter(torch.zeros(len(drop_layers)))
+        elif getattr(config, "merge_module", "no_merge") != "no_merge":
+            raise ValueError(f"Invalid merge module name: {config.merge_module}")
 
     @torch.no_grad()
     def forward(self, input_ids=None, inputs_embeds=None, cache_params=None, pdrop=None, group=None, mixer_ops=None):
@@ -330,13 +356,21 @@ class HybridPrefillStack(nn.Module):
                 vi = pdrop["first_vision_token_position"]
                 att = layer.mixer if layer.block_type == "attention" else None
                 if sharded:
+                    if self.merge_modules is not None:
+                        raise NotImplementedError("the TransV merge module over a sequence-sharded sample is not built")
                     h, offs = sharded_pdrop(h, offs, group, st, kinds[st], ratios, att, vi, pdrop["num_vision_tokens"],
                                             pdrop["text_prompt_len"], trace=pdrop.get("_trace"))
                     lens = [offs[r + 1] - offs[r] for r in range(len(offs) - 1)]
                 else:
                     top, start = pdrop_select(h[0], st, kinds[st], ratios, att, vi, pdrop["num_vision_tokens"],
                                               pdrop["text_prompt_len"])
-                    h = torch.cat([h[:, :vi], h[:, top], h[:, start:]], dim=1)             # :1981-1988
+                    text = h[:, start:]
+                    if self.merge_modules is not None:                                     # TransV: merge_dropped_information
+                        keep_mask = torch.ones(start - vi, dtype=torch.bool, device=h.device)
+                        keep_mask[top - vi] = False
+                        text = text + torch.tanh(self.alpha[st]).to(h.dtype) * cross_attention(
+                            self.merge_modules[st], text, h[:, vi:start][:, keep_mask])
+                    h = torch.cat([h[:, :vi], h[:, top], text], dim=1)                     # :1981-1988
                     if pdrop.get("_trace") is not None:     # tests: the surviving vision positions of this stage
                         pdrop["_trace"].append(top.cpu().clone())
                 pos = torch.arange(h.shape[1])
