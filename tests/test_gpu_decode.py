@@ -128,3 +128,25 @@ def test_decode_continues_our_own_prefill(tv, dtype):
     assert relerr(step, full[:, L:]) < tol
     assert relerr(cache.ssm_states[0], full_cache.ssm_states[0]) < tol
     assert relerr(cache.conv_states[0], full_cache.conv_states[0]) < 1e-5 + (tol if dtype == torch.bfloat16 else 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_decode_step_graph_equals_eager_decode(tv, dtype):
+    """The one-launch (CUDA graph) decode step gives bit-identical outputs and states to the eager one over several tokens."""
+    torch.manual_seed(5)
+    cfg = tv.Mamba2Config(hidden_size=256, mamba_num_heads=16, mamba_head_dim=80, n_groups=2, ssm_state_size=128, chunk_size=128)
+    p = R.nemotron_random_params(cfg.hidden_size, 16, 80, 2, 128)
+    mixer = tv.Mamba2MixerPrefill(cfg).to(dtype).cuda()
+    mixer.load_state_dict({k: v.to(dtype) for k, v in p.items()}, strict=True)
+    conv0 = torch.randn(1, cfg.conv_dim, 4, device="cuda").to(dtype)
+    ssm0 = torch.randn(1, 16, 80, 128, device="cuda")
+    toks = torch.randn(4, 1, 1, cfg.hidden_size, device="cuda").to(dtype)
+    eager = types.SimpleNamespace(conv_states=[conv0.clone()], ssm_states=[ssm0.clone()], conv_kernel_size=4)
+    graph = types.SimpleNamespace(conv_states=[conv0.clone()], ssm_states=[ssm0.clone()], conv_kernel_size=4)
+    with torch.no_grad():
+        for t in toks:
+            a = mixer.decode_step(t, eager)
+            b = mixer.decode_step_graph(t, graph).clone()
+            assert torch.equal(a, b)
+    assert torch.equal(eager.ssm_states[0], graph.ssm_states[0]) and torch.equal(eager.conv_states[0], graph.conv_states[0])
+    assert not torch.equal(graph.ssm_states[0], ssm0)

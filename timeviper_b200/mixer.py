@@ -279,6 +279,34 @@ class Mamba2MixerPrefill(nn.Module):
         y = self.norm(y.view(b, H * P), gate)                                   # :543
         return self.out_proj(y)[:, None, ...]                                   # :546
 
+    @torch.no_grad()
+    def decode_step_graph(self, hidden_states, cache_params):
+        """``decode_step`` replayed as ONE CUDA graph launch.  A cached token is launch-bound when called eagerly (in_proj,
+        conv update, state update, norm, out_proj + the Python between them: ~100 us of host time for ~15 us of kernels at the
+        9B shape); the graph is captured on first use for this layer's cache tensors (the kernels update them in place, at
+        fixed addresses) and this input shape, and re-captured if either changes.  The returned tensor is the graph's static
+        output: copy it before the next call if it must survive."""
+        conv, ssm = cache_params.conv_states[self.layer_idx], cache_params.ssm_states[self.layer_idx]
+        key = (conv.data_ptr(), ssm.data_ptr(), tuple(hidden_states.shape), hidden_states.dtype)
+        held = self.__dict__.get("_decode_graph")
+        if held is None or held[0] != key:
+            dev = hidden_states.device
+            static_in = hidden_states.clone()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):       # warm-up off the capture, on COPIES of the states (a step mutates them)
+                import types
+                shadow = types.SimpleNamespace(conv_states={self.layer_idx: conv.clone()}, ssm_states={self.layer_idx: ssm.clone()})
+                self.decode_step(static_in, shadow)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):       # capture only records: the real states are first touched by the replay
+                out = self.decode_step(static_in, cache_params)
+            held = self.__dict__["_decode_graph"] = (key, graph, static_in, out)
+        held[2].copy_(hidden_states)
+        held[1].replay()
+        return held[3]
+
     def forward(self, hidden_states, cache_params=None, cache_position=None, attention_mask=None, seq_idx=None):
         if not hidden_states.is_cuda:
             raise RuntimeError("Mamba2MixerPrefill runs on CUDA only: there is no CPU fallback "

@@ -41,3 +41,13 @@ timeit(lambda: tv.selective_state_update(state, x.view(b, H, P), dt[:, :, None].
 y = torch.randn(b, H * P, device="cuda").to(dt_)
 timeit(lambda: tv.rmsnorm_fn(y, nw, None, z=gate, eps=1e-5, group_size=H * P // G, norm_before_gate=False), 3 * H * P * 2,
        "gated rmsnorm (1 row)")
+
+# whole decode step of one layer (in_proj + conv update + state update + norm + out_proj): eager vs one CUDA graph replay
+import types
+cfg = tv.Mamba2Config.nanov2_9b()
+mixer = tv.Mamba2MixerPrefill(cfg).to(dt_).cuda()
+cache = types.SimpleNamespace(conv_states=[conv_state.clone()], ssm_states=[state.clone()], conv_kernel_size=K)
+tok = torch.randn(1, 1, cfg.hidden_size, device="cuda").to(dt_)
+with torch.no_grad():
+    timeit(lambda: mixer.decode_step(tok, cache), 2 * state.numel() * 4, "mixer.decode_step, eager (5 kernels + glue)")
+    timeit(lambda: mixer.decode_step_graph(tok, cache), 2 * state.numel() * 4, "mixer.decode_step_graph (one graph replay)")
