@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TV_ABI_VERSION 3
+#define TV_ABI_VERSION 4
 
 typedef enum { TV_F32 = 0, TV_BF16 = 1 } tv_dtype;
 
@@ -83,6 +83,28 @@ typedef struct {
 } tv_rmsnorm_params;
 
 int tv_gated_rmsnorm_fwd(const tv_rmsnorm_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Residual add + NemotronHRMSNorm of the hybrid layer loop: the end of one block,
+ * `residual + hidden_states` (modeling_nano.py:965), and the pre-norm of the next (:888-904, call :941) in one pass:
+ *   s = dtype(x + residual)   (written to sum_out when given);   out = dtype(w * (s * rsqrt(mean_d(s^2) + eps)))
+ * residual and sum_out may be NULL (plain RMSNorm of x).  x, residual, sum_out, out: (rows, d), unit inner stride.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  const void* residual;        /* (rows, d) or NULL                                              */
+  const void* weight;          /* (d,)                                                           */
+  void* sum_out;               /* (rows, d) or NULL: x + residual, rounded to dtype              */
+  void* out;
+  int64_t rows;
+  int32_t d;
+  int32_t dtype;               /* tv_dtype of every tensor                                       */
+  int64_t x_row_stride, res_row_stride, sum_row_stride, out_row_stride;
+  float eps;
+  int32_t reserved;
+} tv_add_rmsnorm_params;
+
+int tv_add_rmsnorm_fwd(const tv_add_rmsnorm_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * mamba_chunk_scan_combined forward (mamba_ssm 2.2.5 ssd_combined; signature

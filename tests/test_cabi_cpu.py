@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert set(declared) == set(L.EXPORTS)
-    assert lib.tv_abi_version() == L.TV_ABI_VERSION == 3
+    assert lib.tv_abi_version() == L.TV_ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header_sizes():
@@ -38,6 +38,7 @@ def test_struct_layouts_match_header_sizes():
     import timeviper_b200._lib as L
     assert ctypes.sizeof(L.ConvParams) == 6 * 8 + 4 * 4 + 4 * 8 + 2 * 4
     assert ctypes.sizeof(L.RmsnormParams) == 5 * 8 + 8 + 2 * 4 + 3 * 8 + 3 * 4 + 4   # + tail padding
+    assert ctypes.sizeof(L.AddRmsnormParams) == 5 * 8 + 8 + 2 * 4 + 4 * 8 + 2 * 4
     assert ctypes.sizeof(L.SsdParams) == 12 * 8 + 7 * 4 + 4 + 15 * 8 + 2 * 4 + 2 * 4 + 4 * 4
 
 

@@ -122,3 +122,30 @@ def test_transv_merge_module_against_reference_golden():
     out = model(inputs_embeds=torch.from_numpy(z["inputs_embeds"]).cuda(), pdrop=pd)
     ref = torch.from_numpy(z["last_hidden_state"])
     assert out.shape == ref.shape and relerr(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,d", [(257, 4480), (33, 96), (5, 10240)])
+def test_fused_add_rmsnorm_matches_the_eager_norm(dtype, rows, d):
+    """csrc/add_rmsnorm.cu against the eager NemotronHRMSNorm (:888-904) on residual + delta (:965): same rounding points
+    (sum rounded to the activation dtype, fp32 statistics and weight multiply)."""
+    import timeviper_b200 as tv
+    if dtype == torch.float32 and d > 5120:
+        pytest.skip("fp32 rows of more than 5120 elements are not served by the fused kernel")
+    torch.manual_seed(0)
+    x = torch.randn(2, rows, d, device="cuda").to(dtype)
+    res = (torch.randn(2, rows, d, device="cuda") * 3).to(dtype)
+    w = (1 + 0.1 * torch.randn(d, device="cuda")).to(dtype)
+
+    def eager(h):
+        h32 = h.to(torch.float32)
+        return (w.to(torch.float32) * (h32 * torch.rsqrt(h32.pow(2).mean(-1, keepdim=True) + 1e-5))).to(dtype)
+    out, s = tv.ops.add_rmsnorm(x, w, 1e-5, residual=res)
+    assert torch.equal(s, res + x)
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-6
+    assert relerr(out, eager(res + x)) < tol
+    out1, s1 = tv.ops.add_rmsnorm(x, w, 1e-5)
+    assert s1 is x and relerr(out1, eager(x)) < tol
+    # a strided view (rows of a wider tensor) is taken as it is
+    wide = torch.randn(rows, 2 * d, device="cuda").to(dtype)
+    assert relerr(tv.ops.add_rmsnorm(wide[:, :d], w, 1e-5)[0], eager(wide[:, :d])) < tol

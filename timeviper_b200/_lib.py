@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("TV_LIB_PATH") or os.path.join(HERE, "libtimeviper_b20
 
 TV_F32, TV_BF16 = 0, 1
 TV_SSD_FULL, TV_SSD_STATE_ONLY, TV_SSD_DT_ONLY = 0, 1, 2
-TV_ABI_VERSION = 3
+TV_ABI_VERSION = 4
 TV_OK, TV_ERR_INVALID, TV_ERR_UNSUPPORTED, TV_ERR_CUDA, TV_ERR_WORKSPACE = 0, -1, -2, -3, -4
 
 
@@ -28,6 +28,13 @@ class RmsnormParams(C.Structure):
                 ("out", C.c_void_p), ("rows", C.c_int64), ("d", C.c_int32), ("group_size", C.c_int32),
                 ("x_row_stride", C.c_int64), ("z_row_stride", C.c_int64), ("out_row_stride", C.c_int64),
                 ("eps", C.c_float), ("norm_before_gate", C.c_int32), ("dtype", C.c_int32)]
+
+
+class AddRmsnormParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("residual", C.c_void_p), ("weight", C.c_void_p), ("sum_out", C.c_void_p),
+                ("out", C.c_void_p), ("rows", C.c_int64), ("d", C.c_int32), ("dtype", C.c_int32),
+                ("x_row_stride", C.c_int64), ("res_row_stride", C.c_int64), ("sum_row_stride", C.c_int64),
+                ("out_row_stride", C.c_int64), ("eps", C.c_float), ("reserved", C.c_int32)]
 
 
 class SsdParams(C.Structure):
@@ -71,7 +78,7 @@ class SsuParams(C.Structure):
                 ("dtype", C.c_int32), ("state_dtype", C.c_int32)]
 
 
-EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd",
+EXPORTS = ("tv_abi_version", "tv_last_error", "tv_causal_conv1d_fwd", "tv_gated_rmsnorm_fwd", "tv_add_rmsnorm_fwd",
            "tv_ssd_workspace_bytes", "tv_ssd_chunk_scan_fwd", "tv_ssd_kernel_family",
            "tv_ssd_fold_boundary_states", "tv_ssd_fold_boundary_states_p2p", "tv_causal_conv1d_update", "tv_selective_state_update",
            "tv_debug_set_trace", "tv_debug_set_ablate", "tv_debug_launch_count")
@@ -94,6 +101,8 @@ def load():
     lib.tv_causal_conv1d_fwd.restype = C.c_int
     lib.tv_gated_rmsnorm_fwd.argtypes = [C.POINTER(RmsnormParams), C.c_void_p]
     lib.tv_gated_rmsnorm_fwd.restype = C.c_int
+    lib.tv_add_rmsnorm_fwd.argtypes = [C.POINTER(AddRmsnormParams), C.c_void_p]
+    lib.tv_add_rmsnorm_fwd.restype = C.c_int
     lib.tv_ssd_workspace_bytes.argtypes = [C.POINTER(SsdParams)]
     lib.tv_ssd_workspace_bytes.restype = C.c_size_t
     lib.tv_ssd_chunk_scan_fwd.argtypes = [C.POINTER(SsdParams), C.c_void_p, C.c_size_t, C.c_void_p]

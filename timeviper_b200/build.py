@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtimeviper_b200.so")
-SOURCES = ["api.cu", "conv1d.cu", "gated_rmsnorm.cu", "ssd_simt.cu", "ssd_tc.cu", "decode.cu"]
+SOURCES = ["api.cu", "conv1d.cu", "gated_rmsnorm.cu", "add_rmsnorm.cu", "ssd_simt.cu", "ssd_tc.cu", "decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math" if False else "-DTV_NO_FAST_MATH", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]

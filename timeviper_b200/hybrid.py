@@ -13,6 +13,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from . import ops as _ops
 from .mixer import Mamba2MixerPrefill
 
 
@@ -24,11 +25,24 @@ class RMSNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(hidden_size))
         self.variance_epsilon = eps
 
-    def forward(self, hidden_states):
+    def fusable(self, hidden_states):
+        """The one-pass CUDA kernel serves bf16 / fp32 rows of up to 10240 / 5120 elements (``csrc/add_rmsnorm.cu``)."""
+        return (hidden_states.is_cuda and hidden_states.dtype in (torch.bfloat16, torch.float32)
+                and hidden_states.shape[-1] % (16 // hidden_states.element_size()) == 0
+                and hidden_states.shape[-1] <= 128 * 10 * (16 // hidden_states.element_size()))
+
+    def forward(self, hidden_states, residual=None):
+        """norm(hidden_states [+ residual]); with a residual returns (normed, hidden_states + residual)."""
+        if self.fusable(hidden_states):
+            out, summed = _ops.add_rmsnorm(hidden_states, self.weight, self.variance_epsilon, residual)
+            return out if residual is None else (out, summed)
+        if residual is not None:
+            hidden_states = residual + hidden_states
         dtype = hidden_states.dtype
         h = hidden_states.to(torch.float32)
         h = h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
-        return (self.weight.to(torch.float32) * h).to(dtype)
+        out = (self.weight.to(torch.float32) * h).to(dtype)
+        return out if residual is None else (out, hidden_states)
 
 
 class Attention(nn.Module):
@@ -176,11 +190,16 @@ class HybridBlock(nn.Module):
         self.norm = RMSNorm(config.hidden_size, eps=config.layer_norm_epsilon)
         self.mixer = {"mamba": Mamba2MixerPrefill, "attention": Attention, "mlp": MLP}[self.block_type](config, layer_idx)
 
-    def forward(self, hidden_states, cache_params=None, cache_position=None, group=None, mixer_ops=None, lens=None):
+    def forward(self, hidden_states, cache_params=None, cache_position=None, group=None, mixer_ops=None, lens=None,
+                delta=None, defer_add=False):
         """group: the sequence is sharded contiguously over this process group (rank order = token order; `lens`: the shard
         lengths when they are not all equal)."""
-        residual = hidden_states.to(torch.float32) if self.residual_in_fp32 else hidden_states
-        h = self.norm(hidden_states.to(self.norm.weight.dtype))
+        if delta is not None:       # the previous block's output not yet added to its residual: add + norm in one pass
+            h, hidden_states = self.norm(delta, residual=hidden_states)
+            residual = hidden_states
+        else:
+            residual = hidden_states.to(torch.float32) if self.residual_in_fp32 else hidden_states
+            h = self.norm(hidden_states.to(self.norm.weight.dtype))
         sharded = group is not None and dist.get_world_size(group) > 1
         if self.block_type == "mamba":
             if sharded:
@@ -193,6 +212,8 @@ class HybridBlock(nn.Module):
             h = sharded_attention_forward(self.mixer, h, group, lens)
         else:
             h = self.mixer(h)
+        if defer_add:               # the caller fuses `residual + h` into the next norm (HybridPrefillStack.forward)
+            return residual, h
         return residual + h
 
 
@@ -350,8 +371,14 @@ class HybridPrefillStack(nn.Module):
             offs = [0]
             for n_ in lens:
                 offs.append(offs[-1] + n_)
+        # `residual + mixer output` of block i is folded into the pre-norm of block i+1 (one pass instead of ~10 elementwise
+        # ones) whenever the fused kernel serves the dtype; a drop stage needs the materialised sum, so it adds first
+        fuse = (not self.config.residual_in_fp32) and self.norm_f.fusable(h)
+        delta = None
         for i, layer in enumerate(self.layers):
             if pdrop is not None and i in drop_layers:
+                if delta is not None:
+                    h, delta = h + delta, None
                 st = drop_layers.index(i)
                 vi = pdrop["first_vision_token_position"]
                 att = layer.mixer if layer.block_type == "attention" else None
@@ -374,8 +401,11 @@ class HybridPrefillStack(nn.Module):
                     if pdrop.get("_trace") is not None:     # tests: the surviving vision positions of this stage
                         pdrop["_trace"].append(top.cpu().clone())
                 pos = torch.arange(h.shape[1])
-            h = layer(h, cache_params=cache_params, cache_position=pos, group=group if sharded else None, mixer_ops=mixer_ops,
-                      lens=lens)
+            r = layer(h, cache_params=cache_params, cache_position=pos, group=group if sharded else None,
+                      mixer_ops=mixer_ops, lens=lens, delta=delta, defer_add=fuse)
+            h, delta = r if fuse else (r, None)
+        if delta is not None:
+            return self.norm_f(delta, residual=h)[0]
         return self.norm_f(h)
 
 

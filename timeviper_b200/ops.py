@@ -297,6 +297,36 @@ def mamba_dt_cumsum_prepare(x, dt, A, B, chunk_size, dt_bias=None, dt_softplus=F
               want_final=False, workspace_stream=workspace_stream)
 
 
+def add_rmsnorm(x, weight, eps, residual=None):
+    """Residual add + NemotronHRMSNorm in one pass (hybrid layer loop, modeling_nano.py:965 + :888-904):
+    ``s = x + residual`` (rounded to the activation dtype, as the eager code materialises it) and
+    ``out = (weight.float() * (s.float() * rsqrt(mean(s^2) + eps))).to(dtype)``.  Returns ``(out, s)``; with
+    ``residual=None`` it is the plain norm of x and s is x."""
+    _require_cuda(x, weight, residual)
+    shape, d = x.shape, x.shape[-1]
+    vec = 16 // x.element_size()
+
+    def rows(t):
+        t2 = t.reshape(-1, d)
+        return t2 if (t2.stride(-1) == 1 and t2.stride(0) % vec == 0 and t2.data_ptr() % 16 == 0) else t2.contiguous()
+    x2 = rows(x)
+    r2 = None if residual is None else rows(residual.to(x.dtype))
+    if residual is not None and residual.shape != shape:
+        raise ValueError("add_rmsnorm: residual must have the shape of x")
+    weight = weight.to(x.dtype).contiguous()
+    out = torch.empty((x2.shape[0], d), dtype=x.dtype, device=x.device)
+    summed = torch.empty_like(out) if r2 is not None else None
+    if x2.shape[0] == 0:
+        return out.reshape(shape), (x if residual is None else (x + residual))
+    p = L.AddRmsnormParams(x=_ptr(x2), residual=_ptr(r2), weight=_ptr(weight), sum_out=_ptr(summed), out=_ptr(out),
+                           rows=x2.shape[0], d=d, dtype=_dtype_code(x, "add_rmsnorm"), x_row_stride=x2.stride(0),
+                           res_row_stride=0 if r2 is None else r2.stride(0),
+                           sum_row_stride=0 if summed is None else summed.stride(0), out_row_stride=out.stride(0),
+                           eps=float(eps), reserved=0)
+    L.check(L.load().tv_add_rmsnorm_fwd(C.byref(p), _stream(x)), "add_rmsnorm")
+    return out.reshape(shape), (x if summed is None else summed.reshape(shape))
+
+
 def _rank_strided(t):
     """True if t (world, ...) is dense within each rank (only the rank stride may be padded)."""
     return t[0].is_contiguous() if t.shape[0] > 0 else True
