@@ -191,3 +191,19 @@ def test_hybrid_stack_mirrors_the_reference_model_parameters():
     assert all(ref_sd[k].shape == our_sd[k].shape for k in ref_sd)
     missing, unexpected = ours.load_state_dict(ref_sd, strict=True)
     assert not missing and not unexpected
+
+
+def test_hybrid_host_logic_shard_bounds_and_pdrop_schedule():
+    """Host-side pieces of the hybrid stack that need no GPU: balanced shard offsets and the pyramid-drop schedule parser
+    (modeling_nano.py:1469-1477; default schedule of evaluate.py:167-172)."""
+    from timeviper_b200.hybrid import parse_pdrop_type, shard_bounds
+    assert shard_bounds(10, 3) == [0, 4, 7, 10] and shard_bounds(8, 2) == [0, 4, 8] and shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+    kinds, layers, ratios = parse_pdrop_type("uni_14_0.8-attn_21_0.6-attn_30_0.4-attn_39_0.2")
+    assert kinds == ["uni", "attn", "attn", "attn"] and layers == [14, 21, 30, 39] and ratios == [1.0, 0.8, 0.6, 0.4, 0.2]
+    import pytest
+    with pytest.raises(ValueError):
+        parse_pdrop_type("uni_14")
+    import timeviper_b200 as tv
+    pat = tv.Mamba2Config.nanov2_9b_hybrid().hybrid_override_pattern
+    assert len(pat) == 56 and pat.count("*") == 4 and pat.count("M") == 27 and pat.count("-") == 25
+    assert [i for i, c in enumerate(pat) if c == "*"] == [14, 21, 30, 39]
