@@ -215,3 +215,28 @@ def test_transv_merge_oracle_matches_reference_golden():
     assert out.shape == ref.shape and float((out - ref).abs().max() / ref.abs().max()) < 2e-5
     nomerge = np.load(os.path.join(os.path.dirname(__file__), "golden", "pdrop_uni_attn_attn.npz"))["last_hidden_state"]
     assert float(np.abs(nomerge - z["last_hidden_state"]).max()) > 1e-2      # the merge really changes the result
+
+
+def test_oracle_size_independent_properties():
+    """Properties the SSD scan must have whatever the size (the GPU tests use the same ones at full size through
+    tools/lin_check.py): exact linearity in x, independence of the chunk size (it only moves rounding points), and
+    agreement of the chunked form with the token-by-token recurrence."""
+    torch.manual_seed(17)
+    b, L, H, P, G, N = 1, 200, 4, 8, 2, 16
+    x = torch.randn(b, L, H, P, dtype=torch.float64)
+    x2 = torch.randn(b, L, H, P, dtype=torch.float64)
+    dt = torch.randn(b, L, H, dtype=torch.float64) * 0.5
+    A = -torch.rand(H, dtype=torch.float64) * 3 - 0.05
+    B = torch.randn(b, L, G, N, dtype=torch.float64)
+    C = torch.randn(b, L, G, N, dtype=torch.float64)
+    bias = torch.randn(H, dtype=torch.float64) * 0.5 - 1.0
+    kw = dict(dt_bias=bias, dt_softplus=True, dtype=torch.float64)
+    y1, s1 = R.ssd_chunked_ref(x, dt, A, B, C, 32, **kw)
+    y2, s2 = R.ssd_chunked_ref(x2, dt, A, B, C, 32, **kw)
+    y12, s12 = R.ssd_chunked_ref(2.0 * x - 3.0 * x2, dt, A, B, C, 32, **kw)
+    assert float((y12 - (2.0 * y1 - 3.0 * y2)).abs().max()) < 1e-10 and float((s12 - (2.0 * s1 - 3.0 * s2)).abs().max()) < 1e-10
+    for q in (16, 64, 200, 256):                              # chunk size: same function of the inputs
+        yq, sq = R.ssd_chunked_ref(x, dt, A, B, C, q, **kw)
+        assert float((yq - y1).abs().max()) < 1e-10 and float((sq - s1).abs().max()) < 1e-10, q
+    ys, ss = R.ssd_sequential_ref(x, dt, A, B, C, **kw)
+    assert float((ys - y1).abs().max()) < 1e-9 and float((ss - s1).abs().max()) < 1e-9
